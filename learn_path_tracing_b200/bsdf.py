@@ -1,0 +1,22 @@
+"""BSDF selectors of taichi_pathtracer (10_final/bsdf.py:62-110, 6_diffuse/bsdf.py:20-26).
+
+In the reference these classes hold @ti.func device code and are chosen inside propagate_once
+(__main__.py:65-75).  Here the scattering code is hand-written CUDA (csrc/shade_v2.cuh); the classes
+remain as the names driver scripts import and carry the shading-model id handed to pt_render.
+"""
+from . import _lib
+
+
+class DiffuseBSDF:
+    """l *= albedo; rd = normalize(n + uniform_on_sphere) — 6_diffuse/bsdf.py:20-26."""
+    shading_model = _lib.PT_SHADE_V2_DIFFUSE
+
+
+class MetalBSDF:
+    """Schlick F0=albedo, slerp(mirror, lambert, roughness^2) micro-normal — bsdf.py:71-86."""
+    shading_model = _lib.PT_SHADE_V2
+
+
+class DielectricBSDF:
+    """Schlick coin; albedo-tinted refraction / Lambert, else mirror — bsdf.py:89-110."""
+    shading_model = _lib.PT_SHADE_V2

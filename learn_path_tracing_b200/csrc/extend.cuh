@@ -1,0 +1,129 @@
+// extend.cuh — closest-hit queries: World.hit of the reference (10_final/world.py:24-34,
+// legacy 15_module.py:838-848) re-designed as ordered, t-pruned BVH2 traversal over a GPU-built LBVH
+// plus a short list of "global" primitives that are too large for the tree.
+#pragma once
+#include "pt_internal.h"
+#include "pt_math.cuh"
+
+struct Hit {
+    float t;   // -1 on miss
+    int prim;  // -1 on miss
+    float u, v;  // triangle barycentrics of vertices b and c (Moller-Trumbore); 0 for spheres
+};
+
+// Sphere.hit (world.py:43-60) in the REFERENCE'S float32 arithmetic: every operation is an explicitly
+// rounded intrinsic (never contracted into FMA), evaluated in the reference's order, so t is bit-identical
+// to the CPU oracle.  The reference's b = 2*oc.rd, disc = b*b - 4c, t = (-b -+ sqrt(disc))/2 is written
+// in the half-b form, which is exactly equal in binary floating point (scaling by 2 and 4 is exact).
+// Returns false when the discriminant is negative (reference leaves t = -1).
+PT_DEV bool sphere_hit_ref(float3 o, float3 d, float4 cr, float r2, bool transparent, float* t_out) {
+    float ocx = __fsub_rn(o.x, cr.x), ocy = __fsub_rn(o.y, cr.y), ocz = __fsub_rn(o.z, cr.z);
+    float h = __fadd_rn(__fadd_rn(__fmul_rn(ocx, d.x), __fmul_rn(ocy, d.y)), __fmul_rn(ocz, d.z));
+    float c = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(ocx, ocx), __fmul_rn(ocy, ocy)), __fmul_rn(ocz, ocz)), r2);
+    float disc = __fsub_rn(__fmul_rn(h, h), c);
+    if (!(disc >= 0.0f)) return false;
+    float s = __fsqrt_rn(disc);
+    float t = __fsub_rn(-h, s);
+    if (t < PT_EPS && transparent) t = __fadd_rn(-h, s);  // world.py:55-56 far-root rule
+    *t_out = t;
+    return true;
+}
+
+// Moller-Trumbore on precomputed (v0, e1, e2).  Strict inside test like the reference's w1,w2,w3 > 0
+// (15_module.py:928); the reference's plane + sub-triangle-area formulation gives the same t to ~1e-6
+// relative, edge-grazing rays are the "ties excepted" of the parity contract.
+PT_DEV bool triangle_hit_mt(float3 o, float3 d, float3 v0, float3 e1, float3 e2, float* t, float* u, float* v) {
+    float3 pvec = cross(d, e2);
+    float det = dot(e1, pvec);
+    float inv = 1.0f / det;
+    float3 tvec = o - v0;
+    float uu = dot(tvec, pvec) * inv;
+    float3 qvec = cross(tvec, e1);
+    float vv = dot(d, qvec) * inv;
+    float tt = dot(e2, qvec) * inv;
+    *t = tt; *u = uu; *v = vv;
+    return uu > 0.0f && vv > 0.0f && (1.0f - uu - vv) > 0.0f;
+}
+
+struct TraceCounters {
+    unsigned int nodes, prims;
+};
+
+template <bool COUNT>
+PT_DEV void test_prim(const SceneView& sv, int p, float3 o, float3 d, float tmin, Hit& h, float& best,
+                      TraceCounters& tc) {
+    if (COUNT) tc.prims++;
+    float t, u = 0.0f, v = 0.0f;
+    bool ok;
+    if (p < sv.n_sph) {
+        float4 cr = __ldg(&sv.sph_cr[p]);
+        float4 aux = __ldg(&sv.sph_aux[p]);
+        ok = sphere_hit_ref(o, d, cr, aux.x, __float_as_int(aux.y) != 0, &t);
+    } else {
+        const float4* g = sv.tri_geo + 3 * (size_t)(p - sv.n_sph);
+        float4 v0 = __ldg(g), e1 = __ldg(g + 1), e2 = __ldg(g + 2);
+        ok = triangle_hit_mt(o, d, f3(v0), f3(e1), f3(e2), &t, &u, &v);
+    }
+    // closest wins; on exactly equal t the lower primitive id wins (the reference's first-wins order)
+    if (ok && t >= tmin && (t < best || (t == best && p < h.prim))) {
+        best = t;
+        h.t = t; h.prim = p; h.u = u; h.v = v;
+    }
+}
+
+// Ordered traversal with best-t pruning and an explicit stack (LBVH depth is bounded by the 63 Morton
+// bits + log2 of duplicate runs; 64 entries cover every tree the builder can emit for < 2^31 prims).
+template <bool COUNT>
+PT_DEV Hit closest_hit(const SceneView& sv, float3 o, float3 d, float tmin, float tmax, TraceCounters& tc) {
+    Hit h;
+    h.t = -1.0f; h.prim = -1; h.u = 0.0f; h.v = 0.0f;
+    float best = tmax;
+    for (int g = 0; g < sv.n_global; ++g) test_prim<COUNT>(sv, __ldg(&sv.global_prims[g]), o, d, tmin, h, best, tc);
+    if (sv.root == PT_NO_BVH) return h;
+
+    // 1/d with |d| clamped away from zero: keeps lo*inv + oi free of inf - inf = NaN for axis-parallel rays
+    const float3 inv = f3(1.0f / (fabsf(d.x) < 1e-18f ? copysignf(1e-18f, d.x) : d.x),
+                          1.0f / (fabsf(d.y) < 1e-18f ? copysignf(1e-18f, d.y) : d.y),
+                          1.0f / (fabsf(d.z) < 1e-18f ? copysignf(1e-18f, d.z) : d.z));
+    const float3 oi = f3(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
+    int stack[64];
+    int sp = 0;
+    int cur = sv.root;
+    for (;;) {
+        if (cur < 0) {
+            test_prim<COUNT>(sv, ~cur, o, d, tmin, h, best, tc);
+        } else {
+            if (COUNT) tc.nodes++;
+            const float4* n = sv.nodes + 4 * (size_t)cur;
+            const float4 a = __ldg(n), b = __ldg(n + 1), c = __ldg(n + 2), k = __ldg(n + 3);
+            // child 0: min (a.x,a.y,a.z) max (a.w,b.x,b.y); child 1: min (b.z,b.w,c.x) max (c.y,c.z,c.w)
+            float x0 = fmaf(a.x, inv.x, oi.x), x1 = fmaf(a.w, inv.x, oi.x);
+            float y0 = fmaf(a.y, inv.y, oi.y), y1 = fmaf(b.x, inv.y, oi.y);
+            float z0 = fmaf(a.z, inv.z, oi.z), z1 = fmaf(b.y, inv.z, oi.z);
+            float t0a = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+            float t1a = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best));
+            x0 = fmaf(b.z, inv.x, oi.x); x1 = fmaf(c.y, inv.x, oi.x);
+            y0 = fmaf(b.w, inv.y, oi.y); y1 = fmaf(c.z, inv.y, oi.y);
+            z0 = fmaf(c.x, inv.z, oi.z); z1 = fmaf(c.w, inv.z, oi.z);
+            float t0b = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+            float t1b = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best));
+            const bool ha = t0a <= t1a, hb = t0b <= t1b;
+            const int ca = __float_as_int(k.x), cb = __float_as_int(k.y);
+            if (ha && hb) {
+                const bool a_first = t0a <= t0b;
+                stack[sp++] = a_first ? cb : ca;
+                cur = a_first ? ca : cb;
+                continue;
+            } else if (ha) {
+                cur = ca;
+                continue;
+            } else if (hb) {
+                cur = cb;
+                continue;
+            }
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+    }
+    return h;
+}

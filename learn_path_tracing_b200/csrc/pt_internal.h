@@ -1,0 +1,122 @@
+// pt_internal.h — host-side objects behind the opaque handles of include/pt_api.h and the POD
+// "scene view" handed by value to every kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pt_api.h"
+
+// ---------------------------------------------------------------------------------------------
+// HBM layouts (all 16-byte vectorised SoA)
+//
+//  primitive ids      [0, n_sph) spheres, [n_sph, n_sph + n_tri) triangles
+//  sph_cr[n_sph]      float4  cx, cy, cz, r
+//  sph_aux[n_sph]     float4  r*r, bits(transparency), bits(texture_id), 0
+//  sph_mat[2*n_sph]   float4  albedo.rgb, roughness | bits(metallic), ior, bits(transparency), 0   (v2)
+//  tri_geo[3*n_tri]   float4  v0.xyz,_ | e1.xyz,_ | e2.xyz,_            (Moller-Trumbore operands, 48 B)
+//  tri_shade[4*n_tri] float4  n0.xyz,u0 | n1.xyz,v0 | n2.xyz,u1 | v1,u2,v2,bits(texture_id)   (64 B)
+//  nodes[4*n_nodes]   float4  BVH2 node, 64 B: c0.min.xyz,c0.max.x | c0.max.yz,c1.min.xy |
+//                             c1.min.z,c1.max.xyz | bits(child0),bits(child1),0,0
+//                             child >= 0 inner node index, child < 0 leaf with primitive ~child
+//  global_prims[]     int     primitives too large for the LBVH (ground sphere / ground plane), tested first
+//  atlas[W*H]         uint2   x-major; .x = albedo r,g,b + roughness, .y = normal x,y,z + metallic (u8 each)
+//  env[W*H]           float4  x-major rgb
+// ---------------------------------------------------------------------------------------------
+struct SceneView {
+    const float4* sph_cr;
+    const float4* sph_aux;
+    const float4* sph_mat;
+    const float4* tri_geo;
+    const float4* tri_shade;
+    const float4* nodes;
+    const int* global_prims;
+    const uint2* atlas;
+    const int4* tex_areas;
+    const float4* env;
+    const float* lut;  // [3][256]: albedo^2.2, x^2, 2x-1
+    int n_sph, n_tri, n_nodes, n_global;
+    int root;          // child reference of the BVH root (node 0, or a leaf ref), 0x7fffffff = no BVH
+    int tex_W, tex_H, ntex;
+    int env_W, env_H;
+    int4 env_area;
+    int has_env;
+    int legacy_spheres;  // spheres are legacy textured spheres (15_module.py:864-896)
+};
+
+#define PT_NO_BVH 0x7fffffff
+
+struct PtContext {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    // path pool (lazily sized)
+    size_t pool_cap = 0;
+    float4* pool[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // [ping-pong][o, d, thr]
+    float4* hits = nullptr;
+    unsigned long long* counters = nullptr;  // device: see wavefront.cu
+    unsigned long long* counters_host = nullptr;  // pinned mirror ring
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+struct HostMesh {
+    std::vector<float> pos, nrm, uv;
+    std::vector<int32_t> faces;
+};
+
+struct PtScene {
+    PtContext* ctx = nullptr;
+    // host staging (kept until build)
+    std::vector<float> h_sph_cr;
+    std::vector<PtMaterial> h_sph_mat;
+    std::vector<int32_t> h_sph_transparency, h_sph_tex;
+    bool legacy_spheres = false;
+    std::vector<float> h_tri9;           // raw triangle soup (p0,p1,p2) of every mesh, in prim order
+    std::vector<float> h_tri_shade;      // 16 floats per triangle
+    int64_t n_tri = 0;
+    bool device_generated_tris = false;  // pt_scene_set_random_triangles
+    // device
+    float4 *d_sph_cr = nullptr, *d_sph_aux = nullptr, *d_sph_mat = nullptr;
+    float4 *d_tri_geo = nullptr, *d_tri_shade = nullptr, *d_nodes = nullptr;
+    int* d_global = nullptr;
+    uint2* d_atlas = nullptr;
+    int4* d_tex_areas = nullptr;
+    float4* d_env = nullptr;
+    float* d_lut = nullptr;
+    std::vector<int32_t> h_global;
+    int64_t n_nodes = 0;
+    bool built = false;
+    SceneView view{};
+};
+
+void pt_set_error(const char* fmt, ...);
+
+#define PT_CUDA(call)                                                                             \
+    do {                                                                                          \
+        cudaError_t _e = (call);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            pt_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));   \
+            return PT_ERR_CUDA;                                                                   \
+        }                                                                                         \
+    } while (0)
+
+#define PT_REQUIRE(cond, msg)                         \
+    do {                                              \
+        if (!(cond)) {                                \
+            pt_set_error("%s: %s", __func__, msg);    \
+            return PT_ERR_INVALID;                    \
+        }                                             \
+    } while (0)
+
+// lbvh.cu — builds nodes over `n_local` primitives whose ids are listed in d_local_ids (device),
+// given per-primitive AABBs aabb[2*prim] (min|max as float4).  Returns device nodes + root ref.
+int pt_lbvh_build(PtContext* ctx, const float4* d_prim_aabb, const int* d_local_ids, int64_t n_local,
+                  float4** d_nodes_out, int64_t* n_nodes_out, int* root_out);
+
+// wavefront.cu
+int pt_ensure_pool(PtContext* ctx, size_t capacity);

@@ -1,0 +1,436 @@
+// wavefront.cu — the render loop of the reference (10_final/__main__.py:78-87,99-103; legacy
+// 15_module.py:980-1036) as a persistent-pool wavefront on one B200:
+//
+//   pool of P path slots in HBM (SoA float4: origin|pixel, direction|sample+bounce, throughput)
+//   repeat until every sample of every pixel has terminated:
+//     k_extend   one ray segment per live path -> hit record (t, prim, u, v)
+//     k_shade    miss: radiance * throughput -> RED.v4 into the accumulator, slot freed
+//                hit : scatter (v2 / legacy BSDFs), bounce+1; over the depth limit -> slot freed
+//                freed slots immediately start a new camera path (ray generation fused here, sample
+//                ids handed out by one block-aggregated atomic), and live + new paths are written
+//                COMPACTED into the other pool by warp ballot + block prefix sums, survivors first.
+//
+// No host synchronisation inside the loop: queue sizes live on the device, the host only reads a small
+// counter block back every few iterations (asynchronously, one chunk behind) to learn when to stop.
+#include <math.h>
+#include <string.h>
+
+#include "shade.cuh"
+
+#define PT_BLOCK 256
+#define PT_WARPS (PT_BLOCK / 32)
+
+// device counter block (unsigned long long[16])
+#define CNT_NEXT_PATH 0
+#define CNT_SEGMENTS 1
+#define CNT_NODES 2
+#define CNT_PRIMS 3
+#define CNT_QUEUE 8  // [8], [9]: ping-pong queue sizes (low 32 bits used)
+#define CNT_WORDS 16
+
+struct RenderConsts {
+    CameraDev cam;
+    unsigned long long total_paths;
+    int W, H;
+    uint32_t seed, spp_offset;
+    int max_depth, shading_model;
+    float absorptivity, tmin;
+    unsigned pool_cap;
+    int accum_sq;
+};
+
+struct PoolPtrs {
+    float4 *o, *d, *l;
+};
+
+// ------------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(PT_BLOCK)
+k_extend(const SceneView sv, const float4* __restrict__ po, const float4* __restrict__ pd, float4* __restrict__ hits,
+         unsigned long long* __restrict__ counters, int q_in, float tmin) {
+    const unsigned n = (unsigned)counters[CNT_QUEUE + q_in];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        counters[CNT_QUEUE + (q_in ^ 1)] = 0ull;  // the shade kernel that follows appends here
+        atomicAdd(&counters[CNT_SEGMENTS], (unsigned long long)n);
+    }
+    TraceCounters tc;
+    tc.nodes = 0; tc.prims = 0;
+    for (unsigned i = blockIdx.x * PT_BLOCK + threadIdx.x; i < n; i += gridDim.x * PT_BLOCK) {
+        const float4 o = po[i], d = pd[i];
+        const Hit h = closest_hit<COUNT>(sv, f3(o), f3(d), tmin, INFINITY, tc);
+        hits[i] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
+    }
+    if (COUNT) {
+        atomicAdd(&counters[CNT_NODES], (unsigned long long)tc.nodes);
+        atomicAdd(&counters[CNT_PRIMS], (unsigned long long)tc.prims);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool LEGACY>
+__global__ void __launch_bounds__(PT_BLOCK)
+k_shade(const SceneView sv, const RenderConsts rc, const PoolPtrs in, const float4* __restrict__ hits,
+        const PoolPtrs out, unsigned long long* __restrict__ counters, int q_in, float4* __restrict__ accum,
+        float4* __restrict__ accum_sq) {
+    __shared__ unsigned s_want[PT_WARPS], s_alive[PT_WARPS];
+    __shared__ unsigned long long s_new_base;
+    __shared__ unsigned s_granted, s_out_base, s_total_alive;
+
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const unsigned n_in = (unsigned)counters[CNT_QUEUE + q_in];
+    unsigned long long* n_out = &counters[CNT_QUEUE + (q_in ^ 1)];
+    // other blocks bump CNT_NEXT_PATH concurrently: one thread samples it so the loop bound is block-uniform
+    __shared__ int s_remain;
+    if (tid == 0) s_remain = *(volatile unsigned long long*)&counters[CNT_NEXT_PATH] < rc.total_paths;
+    __syncthreads();
+    const bool samples_remain = s_remain != 0;
+    const unsigned bound = samples_remain ? rc.pool_cap : n_in;
+    const unsigned WH = (unsigned)rc.W * (unsigned)rc.H;
+
+    for (unsigned base = blockIdx.x * PT_BLOCK; base < bound; base += gridDim.x * PT_BLOCK) {
+        const unsigned i = base + tid;
+        bool alive = false;
+        PathState p;
+        if (i < n_in) {
+            const float4 o = in.o[i], d = in.d[i], l = in.l[i], hr = hits[i];
+            p.o = f3(o); p.d = f3(d); p.l = f3(l);
+            p.pixel = __float_as_uint(o.w);
+            const uint32_t sb = __float_as_uint(d.w);
+            p.sample = sb & 0xFFFFFFu;
+            p.bounce = sb >> 24;
+            Hit h;
+            h.t = hr.x; h.prim = __float_as_int(hr.y); h.u = hr.z; h.v = hr.w;
+            if (h.prim < 0) {
+                // miss: the only light source (sky gradient / environment map), __main__.py:86-87, 15_module.py:990-991
+                const float3 c = (LEGACY ? environment_color(sv, p.d) : sky_color(p.d)) * p.l;
+                if (isfinite(c.x) && isfinite(c.y) && isfinite(c.z)) {
+                    atomicAdd(&accum[p.pixel], make_float4(c.x, c.y, c.z, 1.0f));
+                    if (rc.accum_sq) atomicAdd(&accum_sq[p.pixel], make_float4(c.x * c.x, c.y * c.y, c.z * c.z, 1.0f));
+                }
+            } else {
+                if (LEGACY) scatter_legacy(sv, p, h, rc.absorptivity, rc.seed);
+                else scatter_v2(sv, p, h, rc.shading_model, rc.seed);
+                p.bounce += 1u;
+                alive = p.bounce < (uint32_t)rc.max_depth;  // paths over propagate_limit contribute nothing
+            }
+        }
+        // ---- regeneration + compaction ------------------------------------------------------
+        const bool want = !alive && samples_remain && i < rc.pool_cap;
+        const unsigned wmask = __ballot_sync(0xffffffffu, want);
+        const unsigned amask = __ballot_sync(0xffffffffu, alive);
+        const unsigned lt = (1u << lane) - 1u;
+        unsigned want_rank = __popc(wmask & lt), alive_rank = __popc(amask & lt);
+        if (lane == 0) { s_want[warp] = __popc(wmask); s_alive[warp] = __popc(amask); }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned tw = 0, ta = 0;
+#pragma unroll
+            for (int w = 0; w < PT_WARPS; ++w) { tw += s_want[w]; ta += s_alive[w]; }
+            unsigned granted = 0;
+            unsigned long long nb = 0;
+            if (tw) {
+                nb = atomicAdd(&counters[CNT_NEXT_PATH], (unsigned long long)tw);
+                if (nb < rc.total_paths) {
+                    const unsigned long long left = rc.total_paths - nb;
+                    granted = left < tw ? (unsigned)left : tw;
+                }
+            }
+            s_new_base = nb;
+            s_granted = granted;
+            s_total_alive = ta;
+            s_out_base = (ta + granted) ? (unsigned)atomicAdd(n_out, (unsigned long long)(ta + granted)) : 0u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < PT_WARPS; ++w) {
+            if (w < (int)warp) { want_rank += s_want[w]; alive_rank += s_alive[w]; }
+        }
+        unsigned slot = 0xffffffffu;
+        if (alive) {
+            slot = s_out_base + alive_rank;
+        } else if (want && want_rank < s_granted) {
+            // Camera.get_rays for path id -> (sample, pixel); fused ray generation
+            const unsigned long long pid = s_new_base + want_rank;
+            const uint32_t smp = (uint32_t)(pid / WH);
+            const uint32_t pix = (uint32_t)(pid - (unsigned long long)smp * WH);
+            p.pixel = pix;
+            p.sample = rc.spp_offset + smp;
+            p.bounce = 0u;
+            p.l = f3(1.0f, 1.0f, 1.0f);
+            const float4 u = rng4(p.pixel, p.sample, 0u, rc.seed);
+            camera_ray(rc.cam, (int)(pix % (unsigned)rc.W), (int)(pix / (unsigned)rc.W), u, &p.o, &p.d);
+            slot = s_out_base + s_total_alive + want_rank;
+        }
+        if (slot != 0xffffffffu) {
+            out.o[slot] = make_float4(p.o.x, p.o.y, p.o.z, __uint_as_float(p.pixel));
+            out.d[slot] = make_float4(p.d.x, p.d.y, p.d.z, __uint_as_float(p.sample | (p.bounce << 24)));
+            out.l[slot] = make_float4(p.l.x, p.l.y, p.l.z, 0.0f);
+        }
+        __syncthreads();  // shared scratch is reused by the next trip
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(PT_BLOCK)
+k_trace(const SceneView sv, const float4* __restrict__ rays, float4* __restrict__ hits, long long n,
+        unsigned long long* __restrict__ counters) {
+    TraceCounters tc;
+    tc.nodes = 0; tc.prims = 0;
+    const long long i = (long long)blockIdx.x * PT_BLOCK + threadIdx.x;
+    if (i < n) {
+        const float4 o = __ldg(&rays[2 * i]), d = __ldg(&rays[2 * i + 1]);
+        const Hit h = closest_hit<COUNT>(sv, f3(o), f3(d), o.w, d.w, tc);
+        hits[i] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
+    }
+    if (COUNT) {
+        atomicAdd(&counters[CNT_NODES], (unsigned long long)tc.nodes);
+        atomicAdd(&counters[CNT_PRIMS], (unsigned long long)tc.prims);
+    }
+}
+
+__global__ void k_generate_rays(const CameraDev cam, int W, int H, uint32_t sample, uint32_t seed, float4* rays) {
+    const unsigned pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= (unsigned)W * (unsigned)H) return;
+    float3 o, d;
+    camera_ray(cam, (int)(pix % (unsigned)W), (int)(pix / (unsigned)W), rng4(pix, sample, 0u, seed), &o, &d);
+    rays[2 * pix] = make_float4(o.x, o.y, o.z, PT_EPS);
+    rays[2 * pix + 1] = make_float4(d.x, d.y, d.z, INFINITY);
+}
+
+// SURVEY 8d config 5 ray generator: origin on the sphere of radius 1.5 about (.5,.5,.5), target ~ U[0,1)^3
+__global__ void k_random_rays(float4* rays, long long n, uint32_t seed) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float4 a = rng4((uint32_t)k, 1u, 0u, seed), b = rng4((uint32_t)k, 1u, 1u, seed);
+    const float3 s = sample_at_sphere(a.x, a.y);
+    const float3 o = f3(0.5f + 1.5f * s.x, 0.5f + 1.5f * s.y, 0.5f + 1.5f * s.z);
+    const float3 d = normalize(f3(a.z, a.w, b.x) - o);
+    rays[2 * k] = make_float4(o.x, o.y, o.z, PT_EPS);
+    rays[2 * k + 1] = make_float4(d.x, d.y, d.z, INFINITY);
+}
+
+// ------------------------------------------------------------------------------------------------
+static CameraDev make_camera(const PtCamera* c, int W, int H) {
+    CameraDev d;
+    d.pos = make_float3(c->pos[0], c->pos[1], c->pos[2]);
+    d.front = make_float3(c->front[0], c->front[1], c->front[2]);
+    d.right = make_float3(c->right[0], c->right[1], c->right[2]);
+    d.up = make_float3(c->up[0], c->up[1], c->up[2]);
+    d.view_w = c->view_w; d.view_h = c->view_h;
+    d.focal = c->focal_length; d.aperture = c->aperture;
+    d.inv_w = 1.0f / (float)W; d.inv_h = 1.0f / (float)H;
+    return d;
+}
+
+int pt_ensure_pool(PtContext* ctx, size_t capacity) {
+    if (!ctx->counters) {
+        PT_CUDA(cudaMalloc(&ctx->counters, CNT_WORDS * sizeof(unsigned long long)));
+        PT_CUDA(cudaMallocHost(&ctx->counters_host, 4 * CNT_WORDS * sizeof(unsigned long long)));
+        PT_CUDA(cudaEventCreate(&ctx->ev_a));
+        PT_CUDA(cudaEventCreate(&ctx->ev_b));
+        for (int k = 0; k < 4; ++k) PT_CUDA(cudaEventCreateWithFlags(&ctx->ev_chunk[k], cudaEventDisableTiming));
+    }
+    if (capacity <= ctx->pool_cap) return PT_OK;
+    for (int q = 0; q < 2; ++q)
+        for (int a = 0; a < 3; ++a) {
+            if (ctx->pool[q][a]) cudaFree(ctx->pool[q][a]);
+            ctx->pool[q][a] = nullptr;
+        }
+    if (ctx->hits) cudaFree(ctx->hits);
+    ctx->hits = nullptr;
+    ctx->pool_cap = 0;
+    for (int q = 0; q < 2; ++q)
+        for (int a = 0; a < 3; ++a) PT_CUDA(cudaMalloc(&ctx->pool[q][a], capacity * sizeof(float4)));
+    PT_CUDA(cudaMalloc(&ctx->hits, capacity * sizeof(float4)));
+    ctx->pool_cap = capacity;
+    return PT_OK;
+}
+
+static cudaEvent_t get_event(PtContext* ctx, size_t idx) {
+    while (ctx->ev_pool.size() <= idx) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ctx->ev_pool.push_back(e);
+    }
+    return ctx->ev_pool[idx];
+}
+
+extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, const PtRenderParams* p,
+                         void* accum_dev, void* accum_sq_dev, PtStats* stats) {
+    PT_REQUIRE(ctx && s && cam && p && accum_dev, "null argument");
+    if (!s->built) { pt_set_error("pt_render: scene not built"); return PT_ERR_NOT_BUILT; }
+    PT_REQUIRE(p->width > 0 && p->height > 0 && p->spp >= 0, "bad image size / spp");
+    PT_REQUIRE(p->max_depth > 0 && p->max_depth < 256, "max_depth must be in [1,255]");
+    PT_REQUIRE((long long)p->spp_offset + p->spp <= (1 << 24), "sample index must stay below 2^24");
+    PT_REQUIRE((long long)p->width * p->height < (1ll << 31), "image too large");
+    PT_REQUIRE(p->shading_model >= 0 && p->shading_model <= 2, "unknown shading model");
+    const bool legacy = p->shading_model == PT_SHADE_LEGACY;
+    PT_REQUIRE(legacy || (s->view.n_tri == 0 && !s->view.legacy_spheres), "v2 shading models need a v2 sphere scene");
+    PT_REQUIRE(!legacy || s->view.n_sph == 0 || s->view.legacy_spheres, "legacy shading needs legacy (textured) spheres");
+    const bool want_sq = (p->flags & PT_FLAG_ACCUM_SQ) != 0;
+    PT_REQUIRE(!want_sq || accum_sq_dev, "PT_FLAG_ACCUM_SQ needs accum_sq");
+    PT_CUDA(cudaSetDevice(ctx->device));
+
+    const unsigned long long total = (unsigned long long)p->width * p->height * (unsigned long long)p->spp;
+    size_t cap = p->pool_capacity > 0 ? (size_t)p->pool_capacity : (size_t)1 << 22;
+    if (cap > total) cap = (size_t)total;
+    cap = (cap + PT_BLOCK - 1) / PT_BLOCK * PT_BLOCK;
+    if (cap < PT_BLOCK) cap = PT_BLOCK;
+    int rc_pool = pt_ensure_pool(ctx, cap);
+    if (rc_pool) return rc_pool;
+
+    RenderConsts rc;
+    rc.cam = make_camera(cam, p->width, p->height);
+    rc.total_paths = total;
+    rc.W = p->width; rc.H = p->height;
+    rc.seed = p->seed; rc.spp_offset = (uint32_t)p->spp_offset;
+    rc.max_depth = p->max_depth; rc.shading_model = p->shading_model;
+    rc.absorptivity = p->absorptivity;
+    rc.tmin = legacy ? nextafterf(PT_EPS, 1.0f) : PT_EPS;  // legacy accepts t > eps, v2 t >= 1e-4
+    rc.pool_cap = (unsigned)cap;
+    rc.accum_sq = want_sq ? 1 : 0;
+
+    cudaStream_t st = ctx->stream;
+    const bool timing = (p->flags & PT_FLAG_TIMING) != 0;
+    const bool count = (p->flags & PT_FLAG_COUNTERS) != 0;
+    PT_CUDA(cudaMemsetAsync(ctx->counters, 0, CNT_WORDS * sizeof(unsigned long long), st));
+    PT_CUDA(cudaEventRecord(ctx->ev_a, st));
+
+    const unsigned max_blocks = (unsigned)ctx->sm_count * 16u;
+    unsigned n_upper = (unsigned)cap;  // host-side upper bound of the live queue
+    const int CHUNK = 4;
+    int iterations = 0, launches = 0, q = 0;
+    size_t ev_idx = 0;
+    int chunk_id = 0;
+    bool done = false;
+    unsigned long long last[CNT_WORDS];
+    memset(last, 0, sizeof last);
+    if (total == 0) done = true;
+    while (!done) {
+        for (int k = 0; k < CHUNK; ++k) {
+            unsigned blocks = (n_upper + PT_BLOCK - 1) / PT_BLOCK;
+            if (blocks > max_blocks) blocks = max_blocks;
+            if (blocks < 1) blocks = 1;
+            PoolPtrs pin = {ctx->pool[q][0], ctx->pool[q][1], ctx->pool[q][2]};
+            PoolPtrs pout = {ctx->pool[q ^ 1][0], ctx->pool[q ^ 1][1], ctx->pool[q ^ 1][2]};
+            if (timing) cudaEventRecord(get_event(ctx, ev_idx++), st);
+            if (count) k_extend<true><<<blocks, PT_BLOCK, 0, st>>>(s->view, pin.o, pin.d, ctx->hits, ctx->counters, q, rc.tmin);
+            else k_extend<false><<<blocks, PT_BLOCK, 0, st>>>(s->view, pin.o, pin.d, ctx->hits, ctx->counters, q, rc.tmin);
+            if (timing) cudaEventRecord(get_event(ctx, ev_idx++), st);
+            if (legacy) k_shade<true><<<blocks, PT_BLOCK, 0, st>>>(s->view, rc, pin, ctx->hits, pout, ctx->counters, q, (float4*)accum_dev, (float4*)accum_sq_dev);
+            else k_shade<false><<<blocks, PT_BLOCK, 0, st>>>(s->view, rc, pin, ctx->hits, pout, ctx->counters, q, (float4*)accum_dev, (float4*)accum_sq_dev);
+            if (timing) cudaEventRecord(get_event(ctx, ev_idx++), st);
+            q ^= 1;
+            iterations++;
+            launches += 2;
+        }
+        // asynchronous read-back of the counter block, examined one chunk late so the GPU never idles
+        const int slot = chunk_id & 3;
+        unsigned long long* hostc = ctx->counters_host + slot * CNT_WORDS;
+        PT_CUDA(cudaMemcpyAsync(hostc, ctx->counters, CNT_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        PT_CUDA(cudaEventRecord(ctx->ev_chunk[slot], st));
+        if (chunk_id >= 1) {
+            const int pslot = (chunk_id - 1) & 3;
+            PT_CUDA(cudaEventSynchronize(ctx->ev_chunk[pslot]));
+            const unsigned long long* c = ctx->counters_host + pslot * CNT_WORDS;
+            const unsigned long long live = c[CNT_QUEUE + q];  // CHUNK is even: the live queue of a chunk end is index q
+            if (c[CNT_NEXT_PATH] >= total) {
+                n_upper = (unsigned)live;
+                if (live == 0) done = true;
+            }
+        }
+        chunk_id++;
+        PT_CUDA(cudaGetLastError());
+    }
+    PT_CUDA(cudaMemcpyAsync(last, ctx->counters, sizeof last, cudaMemcpyDeviceToHost, st));
+    PT_CUDA(cudaEventRecord(ctx->ev_b, st));
+    PT_CUDA(cudaStreamSynchronize(st));
+    PT_CUDA(cudaGetLastError());
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->paths = total;
+        stats->segments = last[CNT_SEGMENTS];
+        stats->nodes_visited = last[CNT_NODES];
+        stats->prims_tested = last[CNT_PRIMS];
+        cudaEventElapsedTime(&stats->ms_total, ctx->ev_a, ctx->ev_b);
+        stats->iterations = iterations;
+        stats->launches = launches;
+        stats->launches_extend = iterations;
+        stats->launches_shade = iterations;
+        if (timing) {
+            float e = 0, sh = 0;
+            for (size_t k = 0; k + 3 <= ev_idx; k += 3) {
+                float a = 0, b = 0;
+                cudaEventElapsedTime(&a, ctx->ev_pool[k], ctx->ev_pool[k + 1]);
+                cudaEventElapsedTime(&b, ctx->ev_pool[k + 1], ctx->ev_pool[k + 2]);
+                e += a; sh += b;
+            }
+            stats->ms_extend = e;
+            stats->ms_shade = sh;
+            stats->ms_other = stats->ms_total - e - sh;
+        }
+    }
+    return PT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int pt_trace_batch_device(PtContext* ctx, const PtScene* s, const void* rays_dev, int64_t n,
+                                     void* hits_dev, int flags, PtStats* stats) {
+    PT_REQUIRE(ctx && s && (n == 0 || (rays_dev && hits_dev)), "null argument");
+    if (!s->built) { pt_set_error("pt_trace_batch: scene not built"); return PT_ERR_NOT_BUILT; }
+    PT_REQUIRE(n >= 0, "negative ray count");
+    PT_CUDA(cudaSetDevice(ctx->device));
+    int rcp = pt_ensure_pool(ctx, PT_BLOCK);
+    if (rcp) return rcp;
+    cudaStream_t st = ctx->stream;
+    const bool count = (flags & PT_FLAG_COUNTERS) != 0;
+    PT_CUDA(cudaMemsetAsync(ctx->counters, 0, CNT_WORDS * sizeof(unsigned long long), st));
+    PT_CUDA(cudaEventRecord(ctx->ev_a, st));
+    if (n > 0) {
+        const unsigned blocks = (unsigned)((n + PT_BLOCK - 1) / PT_BLOCK);
+        if (count) k_trace<true><<<blocks, PT_BLOCK, 0, st>>>(s->view, (const float4*)rays_dev, (float4*)hits_dev, n, ctx->counters);
+        else k_trace<false><<<blocks, PT_BLOCK, 0, st>>>(s->view, (const float4*)rays_dev, (float4*)hits_dev, n, ctx->counters);
+    }
+    PT_CUDA(cudaEventRecord(ctx->ev_b, st));
+    PT_CUDA(cudaGetLastError());
+    if (stats) {
+        unsigned long long last[CNT_WORDS];
+        PT_CUDA(cudaMemcpyAsync(last, ctx->counters, sizeof last, cudaMemcpyDeviceToHost, st));
+        PT_CUDA(cudaStreamSynchronize(st));
+        memset(stats, 0, sizeof *stats);
+        stats->paths = (uint64_t)n;
+        stats->segments = (uint64_t)n;
+        stats->nodes_visited = last[CNT_NODES];
+        stats->prims_tested = last[CNT_PRIMS];
+        cudaEventElapsedTime(&stats->ms_total, ctx->ev_a, ctx->ev_b);
+        stats->ms_extend = stats->ms_total;
+        stats->launches = n > 0 ? 1 : 0;
+        stats->launches_extend = stats->launches;
+    }
+    return PT_OK;
+}
+
+extern "C" int pt_random_rays_device(PtContext* ctx, void* rays_dev, int64_t n, uint32_t seed) {
+    PT_REQUIRE(ctx && (n == 0 || rays_dev) && n >= 0, "bad argument");
+    PT_CUDA(cudaSetDevice(ctx->device));
+    if (n > 0) k_random_rays<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((float4*)rays_dev, n, seed);
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+extern "C" int pt_generate_rays(PtContext* ctx, const PtCamera* cam, int width, int height, int sample,
+                                uint32_t seed, float* rays_host) {
+    PT_REQUIRE(ctx && cam && rays_host && width > 0 && height > 0, "bad argument");
+    PT_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)width * height;
+    float4* d = nullptr;
+    PT_CUDA(cudaMalloc(&d, n * 2 * sizeof(float4)));
+    k_generate_rays<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(make_camera(cam, width, height), width, height,
+                                                                         (uint32_t)sample, seed, d);
+    cudaError_t e = cudaMemcpyAsync(rays_host, d, n * 2 * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    PT_CUDA(e);
+    return PT_OK;
+}

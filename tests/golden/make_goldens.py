@@ -1,0 +1,32 @@
+"""Regenerates tests/golden/*_320x180.png from the reference's committed renders.
+
+Run in the build container (where /root/reference is mounted):
+    python tests/golden/make_goldens.py [/root/reference]
+Each golden is the reference's outputs/<stage>.png (1280x720, 8192 spp, ACES + gamma, 8 bit) box-
+filtered 4x4 down to 320x180 so the CPU oracle can be checked against it in seconds.  The PNGs are
+the reference's own output data (not source code); they pin camera, Sphere.hit incl. the far-root
+rule, the v2 BSDFs, the sky, post-processing and imwrite orientation.
+"""
+import os
+import sys
+
+import numpy as np
+from PIL import Image
+
+STAGES = ["6_diffuse", "7_reflect", "8_refract", "9_dof"]
+
+
+def main(ref="/root/reference"):
+    here = os.path.dirname(os.path.abspath(__file__))
+    for s in STAGES:
+        a = np.asarray(Image.open(os.path.join(ref, "outputs", s + ".png")).convert("RGB"), np.float64)
+        h, w, _ = a.shape
+        assert (w, h) == (1280, 720), (s, w, h)
+        b = a.reshape(h // 4, 4, w // 4, 4, 3).mean(axis=(1, 3))
+        out = os.path.join(here, f"{s}_320x180.png")
+        Image.fromarray(np.round(b).astype(np.uint8)).save(out, optimize=True)
+        print(out, os.path.getsize(out), "bytes")
+
+
+if __name__ == "__main__":
+    main(*sys.argv[1:])

@@ -1,0 +1,55 @@
+"""Pins the CPU oracle against the reference's own committed renders:
+outputs/{6_diffuse,7_reflect,8_refract,9_dof}.png, box-filtered to 320x180 (tests/golden/make_goldens.py).
+These pin camera (pinhole + thin lens), Sphere.hit incl. the far-root rule, the v2 BSDFs, the sky,
+ACES + gamma and the imwrite orientation."""
+import os
+
+import numpy as np
+import pytest
+from PIL import Image
+
+import learn_path_tracing_b200 as L
+from learn_path_tracing_b200 import scenes
+from conftest import GOLDEN
+
+CASES = [("6_diffuse", L.PT_SHADE_V2_DIFFUSE), ("7_reflect", L.PT_SHADE_V2), ("8_refract", L.PT_SHADE_V2),
+         ("9_dof", L.PT_SHADE_V2)]
+
+
+@pytest.mark.parametrize("name,model", CASES)
+def test_oracle_matches_reference_render(oracle, name, model):
+    W, H, SPP = 320, 180, 192
+    world, cam = scenes.SCENES[name]((W, H))
+    acc, _, st = oracle.render(oracle.scene_from_world(world), cam.to_struct(), W, H, SPP, 32, model, seed=3)
+    img = L.to_uint8(oracle.postprocess(acc, 1.0 / SPP, aces=True, gamma=2.2)).astype(np.float64)
+    gold = np.asarray(Image.open(os.path.join(GOLDEN, f"{name}_320x180.png")).convert("RGB"), np.float64)
+    d = img - gold
+    rmse, bias = float(np.sqrt((d**2).mean())), float(d.mean())
+    # measured at 256 spp: rmse 1.6-2.5 / 255, |bias| < 0.1; a flipped image gives rmse ~90
+    assert rmse < 3.5, (name, rmse)
+    assert abs(bias) < 0.5, (name, bias)
+    assert st.paths == W * H * SPP
+
+
+def test_segments_per_path_matches_survey(oracle):
+    """8_refract averages 2.33 ray segments per path."""
+    world, cam = scenes.scene_8_refract((160, 90))
+    _, _, st = oracle.render(oracle.scene_from_world(world), cam.to_struct(), 160, 90, 32, 32, L.PT_SHADE_V2, seed=1)
+    assert abs(st.segments / st.paths - 2.33) < 0.05
+
+
+def test_postprocess_matches_python_surface(oracle):
+    rng = np.random.default_rng(0)
+    a = rng.random((8, 5, 3), dtype=np.float32) * 2.0
+    ref = L.gamma_correction(L.ACES_tonemapping(a), 2.2)
+    out = oracle.postprocess(a, 1.0, aces=True, gamma=2.2)
+    assert np.allclose(out, ref, rtol=2e-5, atol=2e-6)
+
+
+def test_rng_is_counter_based_and_uniform(oracle):
+    a = oracle.rng4(5, 7, 1, 99)
+    b = oracle.rng4(5, 7, 1, 99)
+    assert np.array_equal(a, b) and np.all((a >= 0) & (a < 1))
+    assert not np.array_equal(a, oracle.rng4(5, 7, 2, 99))
+    u = np.stack([oracle.rng4(i, 0, 0, 1) for i in range(4096)])
+    assert abs(u.mean() - 0.5) < 0.01 and abs(u.var() - 1 / 12) < 0.005
