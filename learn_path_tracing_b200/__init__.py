@@ -12,12 +12,13 @@ from .camera import Camera
 from .dtypes import HitRecord, Mat3f, Material, Ray, Sphere, Vec2f, Vec2i, Vec3f
 from .image_io import imread, imwrite, to_uint8
 from .postprocessing import ACES_tonemapping, gamma_correction
+from .multigpu import reduce_accumulators, render_distributed, split_samples
 from .render import Renderer, default_context, render
 from .world import World
 
 __all__ = [
     "Context", "Scene", "PtError", "Camera", "World", "Sphere", "Material", "Ray", "HitRecord", "Vec2f", "Vec2i",
     "Vec3f", "Mat3f", "MetalBSDF", "DielectricBSDF", "DiffuseBSDF", "ACES_tonemapping", "gamma_correction",
-    "Renderer", "render", "default_context", "imwrite", "imread", "to_uint8", "PT_SHADE_V2", "PT_SHADE_V2_DIFFUSE",
+    "Renderer", "render", "default_context", "render_distributed", "split_samples", "reduce_accumulators", "imwrite", "imread", "to_uint8", "PT_SHADE_V2", "PT_SHADE_V2_DIFFUSE",
     "PT_SHADE_LEGACY", "PT_FLAG_ACCUM_SQ", "PT_FLAG_TIMING", "PT_FLAG_COUNTERS",
 ]
