@@ -168,7 +168,8 @@ def run_ours(args):
 
     def step(flags=0):
         r.clear()
-        st = r.render(scene, cs, spp, depth, L.PT_SHADE_V2, seed=1, spp_offset=rank * spp, flags=flags)
+        st = r.render(scene, cs, spp, depth, L.PT_SHADE_V2, seed=1, spp_offset=rank * spp, flags=flags, mode=args.mode,
+                      pool_capacity=args.pool, segments_per_launch=args.k)
         if world_size > 1:
             dist.reduce(r.accum, dst=0, op=dist.ReduceOp.SUM)
         return st
@@ -239,7 +240,9 @@ def run_ours(args):
         ms_sh = float(sum(s.ms_shade for s in stats))
         n_ext = int(sum(s.launches_extend for s in stats))
         n_sh = int(sum(s.launches_shade for s in stats))
-        if ms_sh >= ms_ext:
+        if n_ext == 0:  # fused wavefront: one kernel runs extend + shade + regeneration + compaction
+            kname, bytes_k, ms_k, n_k = "k_paths", 160.0 * seg_rank0 + B_PER_PATH * paths_rank0, ms_sh, n_sh
+        elif ms_sh >= ms_ext:
             kname, bytes_k, ms_k, n_k = "k_shade", B_SHADE_SEG * seg_rank0 + B_PER_PATH * paths_rank0, ms_sh, n_sh
         else:
             kname, bytes_k, ms_k, n_k = "k_extend", B_EXTEND_SEG * seg_rank0, ms_ext, n_ext
@@ -249,14 +252,14 @@ def run_ours(args):
             fp32_peak = ctx.measure_fp32_peak()
         except Exception:
             fp32_peak = None
-        cpu = cpu_baseline_run(world, cam, W, H, depth, 12.0)
+        cpu = cpu_baseline_run(world, cam, W, H, depth, 0.5 if args.no_cpu else 12.0)
         line = {
             "metric": "Mpaths/s", "value": paths_total / (t_max * 1e-3) / 1e6, "unit": "Mpaths/s",
             "n_gpus": world_size, "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": t_max / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "scene": WORKLOADS[args.workload][0], "width": W, "height": H,
                        "spp_per_gpu": spp, "max_depth": depth, "parallelism": f"sample-split x{world_size} + NCCL reduce",
-                       "l2": "flushed between timed steps (252 MB fill); path pool 470 MB > 126 MB L2"},
+                       "l2": "flushed between timed steps (252 MB fill)", "mode": int(stats[0].reserved[0])},
             "mrays_per_s": seg_total / (t_max * 1e-3) / 1e6,
             "segments_per_path": seg_rank0 / paths_rank0,
             "e2e": e2e,
@@ -265,7 +268,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
                          "launches": n_k, "avg_launch_ms": ms_k / max(n_k, 1),
-                         "algorithmic_bytes": "k_shade 112 B/segment + 24 B/path; k_extend 48 B/segment (SURVEY 8d)",
+                         "algorithmic_bytes": "160 B/segment + 24 B/path for the whole wavefront step (k_paths); split mode: k_shade 112 B/segment + 24 B/path, k_extend 48 B/segment (SURVEY 8d)",
                          "whole_render_160B_per_segment": {"achieved": whole, "frac": whole / peak},
                          "kernel_ms": {"k_extend": ms_ext / K, "k_shade": ms_sh / K, "step": t_local / K}},
             "fp32_peak_tflops_measured": fp32_peak,
@@ -287,6 +290,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="8_refract_1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", type=int, default=0, help="wavefront mode: 0 auto (fused), 1 split kernels, 2 fused")
+    ap.add_argument("--pool", type=int, default=0, help="path-pool slots (0 = library default)")
+    ap.add_argument("--k", type=int, default=0, help="fused mode: segments per launch (0 = default)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -22,6 +22,10 @@ PT_FLAG_ACCUM_SQ = 1
 PT_FLAG_TIMING = 2
 PT_FLAG_COUNTERS = 4
 
+PT_MODE_AUTO = 0
+PT_MODE_SPLIT = 1   # classic wavefront: k_extend + k_shade per bounce, pool refilled by an atomic counter
+PT_MODE_FUSED = 2   # k_paths: K segments per launch in registers, compaction at write-back (default)
+
 
 class PtMaterial(C.Structure):
     _fields_ = [("albedo", C.c_float * 3), ("roughness", C.c_float), ("metallic", C.c_int32),

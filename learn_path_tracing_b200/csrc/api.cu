@@ -432,9 +432,25 @@ extern "C" int pt_scene_build(PtScene* s) {
     // global primitives + LBVH over the rest
     select_global_prims(s, n_total, s->h_global);
     const int64_t n_local = n_total - (int64_t)s->h_global.size();
-    if (!s->h_global.empty()) {
-        PT_CUDA(cudaMalloc(&s->d_global, s->h_global.size() * sizeof(int)));
-        PT_CUDA(cudaMemcpy(s->d_global, s->h_global.data(), s->h_global.size() * sizeof(int), cudaMemcpyHostToDevice));
+    // global spheres go inline into the kernel parameters, other global primitives into a small device list
+    std::vector<int32_t> listed;
+    SceneView& vw = s->view;
+    vw.n_inl = 0;
+    for (int32_t p : s->h_global) {
+        if (p < n_sph && vw.n_inl < PT_MAX_INLINE) {
+            const int k = vw.n_inl++;
+            const float* c = &s->h_sph_cr[4 * (size_t)p];
+            vw.inl_id[k] = p;
+            vw.inl_transparent[k] = s->h_sph_transparency[p];
+            vw.inl_r2[k] = c[3] * c[3];
+            vw.inl_cr[k] = make_float4(c[0], c[1], c[2], c[3]);
+        } else {
+            listed.push_back(p);
+        }
+    }
+    if (!listed.empty()) {
+        PT_CUDA(cudaMalloc(&s->d_global, listed.size() * sizeof(int)));
+        PT_CUDA(cudaMemcpy(s->d_global, listed.data(), listed.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
     int root = PT_NO_BVH;
     s->n_nodes = 0;
@@ -466,7 +482,7 @@ extern "C" int pt_scene_build(PtScene* s) {
     v.sph_cr = s->d_sph_cr; v.sph_aux = s->d_sph_aux; v.sph_mat = s->d_sph_mat;
     v.tri_geo = s->d_tri_geo; v.tri_shade = s->d_tri_shade;
     v.nodes = s->d_nodes; v.global_prims = s->d_global;
-    v.n_sph = (int)n_sph; v.n_tri = (int)n_tri; v.n_nodes = (int)s->n_nodes; v.n_global = (int)s->h_global.size();
+    v.n_sph = (int)n_sph; v.n_tri = (int)n_tri; v.n_nodes = (int)s->n_nodes; v.n_global = (int)listed.size();
     v.root = root;
     v.legacy_spheres = s->legacy_spheres ? 1 : 0;
     s->built = true;

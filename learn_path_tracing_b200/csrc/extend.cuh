@@ -78,6 +78,20 @@ PT_DEV Hit closest_hit(const SceneView& sv, float3 o, float3 d, float tmin, floa
     Hit h;
     h.t = -1.0f; h.prim = -1; h.u = 0.0f; h.v = 0.0f;
     float best = tmax;
+    // global spheres straight from the parameter (constant) bank
+#pragma unroll
+    for (int g = 0; g < PT_MAX_INLINE; ++g) {
+        if (g < sv.n_inl) {
+            if (COUNT) tc.prims++;
+            float t;
+            const int p = sv.inl_id[g];
+            if (sphere_hit_ref(o, d, sv.inl_cr[g], sv.inl_r2[g], sv.inl_transparent[g] != 0, &t) && t >= tmin &&
+                (t < best || (t == best && p < h.prim))) {
+                best = t;
+                h.t = t; h.prim = p;
+            }
+        }
+    }
     for (int g = 0; g < sv.n_global; ++g) test_prim<COUNT>(sv, __ldg(&sv.global_prims[g]), o, d, tmin, h, best, tc);
     if (sv.root == PT_NO_BVH) return h;
 

@@ -22,10 +22,12 @@
 //  nodes[4*n_nodes]   float4  BVH2 node, 64 B: c0.min.xyz,c0.max.x | c0.max.yz,c1.min.xy |
 //                             c1.min.z,c1.max.xyz | bits(child0),bits(child1),0,0
 //                             child >= 0 inner node index, child < 0 leaf with primitive ~child
-//  global_prims[]     int     primitives too large for the LBVH (ground sphere / ground plane), tested first
+//  global_prims[]     int     primitives too large for the LBVH (ground plane triangles), tested first;
+//                             global SPHERES are passed inline in the kernel parameters instead (SceneView::inl_*)
 //  atlas[W*H]         uint2   x-major; .x = albedo r,g,b + roughness, .y = normal x,y,z + metallic (u8 each)
 //  env[W*H]           float4  x-major rgb
 // ---------------------------------------------------------------------------------------------
+#define PT_MAX_INLINE 8
 struct SceneView {
     const float4* sph_cr;
     const float4* sph_aux;
@@ -45,6 +47,13 @@ struct SceneView {
     int4 env_area;
     int has_env;
     int legacy_spheres;  // spheres are legacy textured spheres (15_module.py:864-896)
+    // "global" spheres (ground sphere; every sphere of a <= 8 primitive scene) live in the kernel parameter
+    // bank: the brute-force loop reads them as constant operands, no loads at all
+    int n_inl;
+    int inl_id[PT_MAX_INLINE];
+    int inl_transparent[PT_MAX_INLINE];
+    float inl_r2[PT_MAX_INLINE];
+    float4 inl_cr[PT_MAX_INLINE];
 };
 
 #define PT_NO_BVH 0x7fffffff

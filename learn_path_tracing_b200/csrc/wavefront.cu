@@ -12,6 +12,13 @@
 //
 // No host synchronisation inside the loop: queue sizes live on the device, the host only reads a small
 // counter block back every few iterations (asynchronously, one chunk behind) to learn when to stop.
+//
+// That split form (one launch per stage per bounce, 160 B of HBM traffic per segment) is kept as
+// PT_MODE_SPLIT.  ncu showed both of its kernels issue-/latency-bound rather than HBM-bound
+// (profiles/r01_*_split_*), so the default is the FUSED form, k_paths: the same stages, but a path stays
+// in registers for up to K segments per launch (extend -> shade -> regenerate in place), and only the
+// survivors of a launch go through the ballot/prefix-sum compaction into the HBM pool.  Sample ids are
+// strided statically (path id, id + P, id + 2P, ... per pool slot), so regeneration needs no atomics.
 #include <math.h>
 #include <string.h>
 
@@ -27,6 +34,12 @@
 #define CNT_PRIMS 3
 #define CNT_QUEUE 8  // [8], [9]: ping-pong queue sizes (low 32 bits used)
 #define CNT_WORDS 16
+#define CNT_LIVE 16  // fused mode: live-path count after launch L at [CNT_LIVE + L]
+#define PT_MAX_LAUNCHES 4080
+#define CNT_TOTAL_WORDS (CNT_LIVE + PT_MAX_LAUNCHES)
+#define PT_MODE_AUTO 0
+#define PT_MODE_SPLIT 1
+#define PT_MODE_FUSED 2
 
 struct RenderConsts {
     CameraDev cam;
@@ -37,6 +50,9 @@ struct RenderConsts {
     float absorptivity, tmin;
     unsigned pool_cap;
     int accum_sq;
+    // fused mode: static striding of path ids over the pool, id -> (sample, pixel) without division
+    uint32_t stride_samples, stride_pixels;  // pool_cap = stride_samples * W*H + stride_pixels
+    uint32_t sample_end;                     // spp_offset + spp
 };
 
 struct PoolPtrs {
@@ -170,6 +186,112 @@ k_shade(const SceneView sv, const RenderConsts rc, const PoolPtrs in, const floa
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fused wavefront step: up to K ray segments per path slot per launch, state in registers.
+PT_DEV void start_path(const RenderConsts& rc, PathState& p, uint32_t pixel, uint32_t sample) {
+    p.pixel = pixel;
+    p.sample = sample;
+    p.bounce = 0u;
+    p.l = f3(1.0f, 1.0f, 1.0f);
+    const float4 u = rng4(pixel, sample, 0u, rc.seed);
+    const uint32_t j = pixel / (uint32_t)rc.W;
+    camera_ray(rc.cam, (int)(pixel - j * (uint32_t)rc.W), (int)j, u, &p.o, &p.d);
+}
+
+template <bool LEGACY, bool COUNT>
+__global__ void __launch_bounds__(PT_BLOCK, 4)
+k_paths(const SceneView sv, const RenderConsts rc, const PoolPtrs in, const PoolPtrs out,
+        unsigned long long* __restrict__ counters, int launch, int K, float4* __restrict__ accum,
+        float4* __restrict__ accum_sq) {
+    __shared__ unsigned s_alive[PT_WARPS];
+    __shared__ unsigned s_out_base;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const unsigned i = blockIdx.x * PT_BLOCK + tid;
+    const unsigned WH = (unsigned)rc.W * (unsigned)rc.H;
+    PathState p;
+    bool alive = false;
+    if (launch == 0) {  // slot i starts the id sequence i, i + P, i + 2P, ...
+        if (i < rc.pool_cap) {
+            const uint32_t smp = i / WH;
+            if (smp < rc.sample_end - rc.spp_offset) {
+                start_path(rc, p, i - smp * WH, rc.spp_offset + smp);
+                alive = true;
+            }
+        }
+    } else if (i < (unsigned)counters[CNT_LIVE + launch - 1]) {
+        const float4 o = in.o[i], d = in.d[i], l = in.l[i];
+        p.o = f3(o); p.d = f3(d); p.l = f3(l);
+        p.pixel = __float_as_uint(o.w);
+        const uint32_t sb = __float_as_uint(d.w);
+        p.sample = sb & 0xFFFFFFu;
+        p.bounce = sb >> 24;
+        alive = true;
+    }
+    TraceCounters tc;
+    tc.nodes = 0; tc.prims = 0;
+    unsigned nseg = 0;
+    for (int k = 0; k < K; ++k) {
+        if (!__any_sync(0xffffffffu, alive)) break;
+        if (alive) {
+            const Hit h = closest_hit<COUNT>(sv, p.o, p.d, rc.tmin, INFINITY, tc);  // extend
+            ++nseg;
+            if (h.prim < 0) {  // miss: radiance * throughput into the accumulator, path ends
+                const float3 c = (LEGACY ? environment_color(sv, p.d) : sky_color(p.d)) * p.l;
+                if (isfinite(c.x) && isfinite(c.y) && isfinite(c.z)) {
+                    atomicAdd(&accum[p.pixel], make_float4(c.x, c.y, c.z, 1.0f));
+                    if (rc.accum_sq) atomicAdd(&accum_sq[p.pixel], make_float4(c.x * c.x, c.y * c.y, c.z * c.z, 1.0f));
+                }
+                alive = false;
+            } else {  // shade / scatter
+                if (LEGACY) scatter_legacy(sv, p, h, rc.absorptivity, rc.seed);
+                else scatter_v2(sv, p, h, rc.shading_model, rc.seed);
+                p.bounce += 1u;
+                alive = p.bounce < (uint32_t)rc.max_depth;
+            }
+            if (!alive) {  // regenerate in place: next id of this slot's sequence (fused ray generation)
+                uint32_t pix = p.pixel + rc.stride_pixels, smp = p.sample + rc.stride_samples;
+                if (pix >= WH) { pix -= WH; smp += 1u; }
+                if (smp < rc.sample_end) {
+                    start_path(rc, p, pix, smp);
+                    alive = true;
+                }
+            }
+        }
+    }
+    // ---- compaction of the survivors into the pool: warp ballot + block prefix sum ----------------
+    const unsigned amask = __ballot_sync(0xffffffffu, alive);
+    unsigned rank = __popc(amask & ((1u << lane) - 1u));
+    if (lane == 0) s_alive[warp] = __popc(amask);
+    nseg += __shfl_xor_sync(0xffffffffu, nseg, 16);
+    nseg += __shfl_xor_sync(0xffffffffu, nseg, 8);
+    nseg += __shfl_xor_sync(0xffffffffu, nseg, 4);
+    nseg += __shfl_xor_sync(0xffffffffu, nseg, 2);
+    nseg += __shfl_xor_sync(0xffffffffu, nseg, 1);
+    if (lane == 0 && nseg) atomicAdd(&counters[CNT_SEGMENTS], (unsigned long long)nseg);
+    __syncthreads();
+    if (tid == 0) {
+        unsigned ta = 0;
+#pragma unroll
+        for (int w = 0; w < PT_WARPS; ++w) ta += s_alive[w];
+        s_out_base = ta ? (unsigned)atomicAdd(&counters[CNT_LIVE + launch], (unsigned long long)ta) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < PT_WARPS; ++w)
+        if (w < (int)warp) rank += s_alive[w];
+    if (alive) {
+        const unsigned slot = s_out_base + rank;
+        out.o[slot] = make_float4(p.o.x, p.o.y, p.o.z, __uint_as_float(p.pixel));
+        out.d[slot] = make_float4(p.d.x, p.d.y, p.d.z, __uint_as_float(p.sample | (p.bounce << 24)));
+        out.l[slot] = make_float4(p.l.x, p.l.y, p.l.z, 0.0f);
+    }
+    if (COUNT) {
+        atomicAdd(&counters[CNT_NODES], (unsigned long long)tc.nodes);
+        atomicAdd(&counters[CNT_PRIMS], (unsigned long long)tc.prims);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 template <bool COUNT>
 __global__ void __launch_bounds__(PT_BLOCK)
@@ -225,8 +347,8 @@ static CameraDev make_camera(const PtCamera* c, int W, int H) {
 
 int pt_ensure_pool(PtContext* ctx, size_t capacity) {
     if (!ctx->counters) {
-        PT_CUDA(cudaMalloc(&ctx->counters, CNT_WORDS * sizeof(unsigned long long)));
-        PT_CUDA(cudaMallocHost(&ctx->counters_host, 4 * CNT_WORDS * sizeof(unsigned long long)));
+        PT_CUDA(cudaMalloc(&ctx->counters, CNT_TOTAL_WORDS * sizeof(unsigned long long)));
+        PT_CUDA(cudaMallocHost(&ctx->counters_host, (4 * CNT_WORDS + PT_MAX_LAUNCHES) * sizeof(unsigned long long)));
         PT_CUDA(cudaEventCreate(&ctx->ev_a));
         PT_CUDA(cudaEventCreate(&ctx->ev_b));
         for (int k = 0; k < 4; ++k) PT_CUDA(cudaEventCreateWithFlags(&ctx->ev_chunk[k], cudaEventDisableTiming));
@@ -256,57 +378,17 @@ static cudaEvent_t get_event(PtContext* ctx, size_t idx) {
     return ctx->ev_pool[idx];
 }
 
-extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, const PtRenderParams* p,
-                         void* accum_dev, void* accum_sq_dev, PtStats* stats) {
-    PT_REQUIRE(ctx && s && cam && p && accum_dev, "null argument");
-    if (!s->built) { pt_set_error("pt_render: scene not built"); return PT_ERR_NOT_BUILT; }
-    PT_REQUIRE(p->width > 0 && p->height > 0 && p->spp >= 0, "bad image size / spp");
-    PT_REQUIRE(p->max_depth > 0 && p->max_depth < 256, "max_depth must be in [1,255]");
-    PT_REQUIRE((long long)p->spp_offset + p->spp <= (1 << 24), "sample index must stay below 2^24");
-    PT_REQUIRE((long long)p->width * p->height < (1ll << 31), "image too large");
-    PT_REQUIRE(p->shading_model >= 0 && p->shading_model <= 2, "unknown shading model");
-    const bool legacy = p->shading_model == PT_SHADE_LEGACY;
-    PT_REQUIRE(legacy || (s->view.n_tri == 0 && !s->view.legacy_spheres), "v2 shading models need a v2 sphere scene");
-    PT_REQUIRE(!legacy || s->view.n_sph == 0 || s->view.legacy_spheres, "legacy shading needs legacy (textured) spheres");
-    const bool want_sq = (p->flags & PT_FLAG_ACCUM_SQ) != 0;
-    PT_REQUIRE(!want_sq || accum_sq_dev, "PT_FLAG_ACCUM_SQ needs accum_sq");
-    PT_CUDA(cudaSetDevice(ctx->device));
-
-    const unsigned long long total = (unsigned long long)p->width * p->height * (unsigned long long)p->spp;
-    size_t cap = p->pool_capacity > 0 ? (size_t)p->pool_capacity : (size_t)1 << 22;
-    if (cap > total) cap = (size_t)total;
-    cap = (cap + PT_BLOCK - 1) / PT_BLOCK * PT_BLOCK;
-    if (cap < PT_BLOCK) cap = PT_BLOCK;
-    int rc_pool = pt_ensure_pool(ctx, cap);
-    if (rc_pool) return rc_pool;
-
-    RenderConsts rc;
-    rc.cam = make_camera(cam, p->width, p->height);
-    rc.total_paths = total;
-    rc.W = p->width; rc.H = p->height;
-    rc.seed = p->seed; rc.spp_offset = (uint32_t)p->spp_offset;
-    rc.max_depth = p->max_depth; rc.shading_model = p->shading_model;
-    rc.absorptivity = p->absorptivity;
-    rc.tmin = legacy ? nextafterf(PT_EPS, 1.0f) : PT_EPS;  // legacy accepts t > eps, v2 t >= 1e-4
-    rc.pool_cap = (unsigned)cap;
-    rc.accum_sq = want_sq ? 1 : 0;
-
+// PT_MODE_SPLIT: classic two-kernel wavefront with a dynamically refilled pool.
+static int render_split(PtContext* ctx, const PtScene* s, const RenderConsts& rc, bool legacy, bool timing, bool count,
+                        float4* accum, float4* accum_sq, int* iterations_out, int* launches_out, size_t* ev_idx_out) {
     cudaStream_t st = ctx->stream;
-    const bool timing = (p->flags & PT_FLAG_TIMING) != 0;
-    const bool count = (p->flags & PT_FLAG_COUNTERS) != 0;
-    PT_CUDA(cudaMemsetAsync(ctx->counters, 0, CNT_WORDS * sizeof(unsigned long long), st));
-    PT_CUDA(cudaEventRecord(ctx->ev_a, st));
-
+    const unsigned long long total = rc.total_paths;
     const unsigned max_blocks = (unsigned)ctx->sm_count * 16u;
-    unsigned n_upper = (unsigned)cap;  // host-side upper bound of the live queue
+    unsigned n_upper = rc.pool_cap;  // host-side upper bound of the live queue
     const int CHUNK = 4;
-    int iterations = 0, launches = 0, q = 0;
+    int iterations = 0, launches = 0, q = 0, chunk_id = 0;
     size_t ev_idx = 0;
-    int chunk_id = 0;
-    bool done = false;
-    unsigned long long last[CNT_WORDS];
-    memset(last, 0, sizeof last);
-    if (total == 0) done = true;
+    bool done = total == 0;
     while (!done) {
         for (int k = 0; k < CHUNK; ++k) {
             unsigned blocks = (n_upper + PT_BLOCK - 1) / PT_BLOCK;
@@ -318,8 +400,8 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
             if (count) k_extend<true><<<blocks, PT_BLOCK, 0, st>>>(s->view, pin.o, pin.d, ctx->hits, ctx->counters, q, rc.tmin);
             else k_extend<false><<<blocks, PT_BLOCK, 0, st>>>(s->view, pin.o, pin.d, ctx->hits, ctx->counters, q, rc.tmin);
             if (timing) cudaEventRecord(get_event(ctx, ev_idx++), st);
-            if (legacy) k_shade<true><<<blocks, PT_BLOCK, 0, st>>>(s->view, rc, pin, ctx->hits, pout, ctx->counters, q, (float4*)accum_dev, (float4*)accum_sq_dev);
-            else k_shade<false><<<blocks, PT_BLOCK, 0, st>>>(s->view, rc, pin, ctx->hits, pout, ctx->counters, q, (float4*)accum_dev, (float4*)accum_sq_dev);
+            if (legacy) k_shade<true><<<blocks, PT_BLOCK, 0, st>>>(s->view, rc, pin, ctx->hits, pout, ctx->counters, q, accum, accum_sq);
+            else k_shade<false><<<blocks, PT_BLOCK, 0, st>>>(s->view, rc, pin, ctx->hits, pout, ctx->counters, q, accum, accum_sq);
             if (timing) cudaEventRecord(get_event(ctx, ev_idx++), st);
             q ^= 1;
             iterations++;
@@ -343,6 +425,115 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
         chunk_id++;
         PT_CUDA(cudaGetLastError());
     }
+    *iterations_out = iterations;
+    *launches_out = launches;
+    *ev_idx_out = ev_idx;
+    return PT_OK;
+}
+
+// PT_MODE_FUSED (default): k_paths, K segments per launch in registers, compaction at write-back.
+static int render_fused(PtContext* ctx, const PtScene* s, const RenderConsts& rc, bool legacy, bool timing, bool count,
+                        float4* accum, float4* accum_sq, int K, int* iterations_out, int* launches_out, size_t* ev_idx_out) {
+    cudaStream_t st = ctx->stream;
+    unsigned long long* host_live = ctx->counters_host + 4 * CNT_WORDS;
+    unsigned n_upper = rc.pool_cap;
+    int launch = 0, q = 0, checked = 0;
+    size_t ev_idx = 0;
+    bool done = rc.total_paths == 0;
+    while (!done) {
+        if (launch >= PT_MAX_LAUNCHES) { pt_set_error("pt_render: launch budget exceeded"); return PT_ERR_INVALID; }
+        const unsigned blocks = (n_upper + PT_BLOCK - 1) / PT_BLOCK;
+        PoolPtrs pin = {ctx->pool[q][0], ctx->pool[q][1], ctx->pool[q][2]};
+        PoolPtrs pout = {ctx->pool[q ^ 1][0], ctx->pool[q ^ 1][1], ctx->pool[q ^ 1][2]};
+        if (timing) cudaEventRecord(get_event(ctx, ev_idx++), st);
+        if (legacy) {
+            if (count) k_paths<true, true><<<blocks, PT_BLOCK, 0, st>>>(s->view, rc, pin, pout, ctx->counters, launch, K, accum, accum_sq);
+            else k_paths<true, false><<<blocks, PT_BLOCK, 0, st>>>(s->view, rc, pin, pout, ctx->counters, launch, K, accum, accum_sq);
+        } else {
+            if (count) k_paths<false, true><<<blocks, PT_BLOCK, 0, st>>>(s->view, rc, pin, pout, ctx->counters, launch, K, accum, accum_sq);
+            else k_paths<false, false><<<blocks, PT_BLOCK, 0, st>>>(s->view, rc, pin, pout, ctx->counters, launch, K, accum, accum_sq);
+        }
+        if (timing) cudaEventRecord(get_event(ctx, ev_idx++), st);
+        // live count of this launch -> pinned host memory, examined one launch late (the GPU never waits on the host)
+        PT_CUDA(cudaMemcpyAsync(host_live + launch, ctx->counters + CNT_LIVE + launch, sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, st));
+        PT_CUDA(cudaEventRecord(ctx->ev_chunk[launch & 3], st));
+        q ^= 1;
+        launch++;
+        while (checked + 1 < launch) {  // everything but the launch just submitted
+            PT_CUDA(cudaEventSynchronize(ctx->ev_chunk[checked & 3]));
+            const unsigned long long live = host_live[checked];
+            n_upper = (unsigned)live;  // live counts never grow: id sequences only end
+            if (live == 0) done = true;
+            checked++;
+        }
+        PT_CUDA(cudaGetLastError());
+    }
+    *iterations_out = launch;
+    *launches_out = launch;
+    *ev_idx_out = ev_idx;
+    return PT_OK;
+}
+
+extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, const PtRenderParams* p,
+                         void* accum_dev, void* accum_sq_dev, PtStats* stats) {
+    PT_REQUIRE(ctx && s && cam && p && accum_dev, "null argument");
+    if (!s->built) { pt_set_error("pt_render: scene not built"); return PT_ERR_NOT_BUILT; }
+    PT_REQUIRE(p->width > 0 && p->height > 0 && p->spp >= 0, "bad image size / spp");
+    PT_REQUIRE(p->max_depth > 0 && p->max_depth < 256, "max_depth must be in [1,255]");
+    PT_REQUIRE((long long)p->spp_offset + p->spp <= (1 << 24), "sample index must stay below 2^24");
+    PT_REQUIRE((long long)p->width * p->height < (1ll << 31), "image too large");
+    PT_REQUIRE(p->shading_model >= 0 && p->shading_model <= 2, "unknown shading model");
+    const bool legacy = p->shading_model == PT_SHADE_LEGACY;
+    PT_REQUIRE(legacy || (s->view.n_tri == 0 && !s->view.legacy_spheres), "v2 shading models need a v2 sphere scene");
+    PT_REQUIRE(!legacy || s->view.n_sph == 0 || s->view.legacy_spheres, "legacy shading needs legacy (textured) spheres");
+    const bool want_sq = (p->flags & PT_FLAG_ACCUM_SQ) != 0;
+    PT_REQUIRE(!want_sq || accum_sq_dev, "PT_FLAG_ACCUM_SQ needs accum_sq");
+    const int mode = p->reserved[0] == PT_MODE_SPLIT ? PT_MODE_SPLIT : PT_MODE_FUSED;
+    PT_REQUIRE(p->reserved[0] >= 0 && p->reserved[0] <= 2, "reserved[0] (wavefront mode) must be 0, 1 or 2");
+    PT_REQUIRE(p->reserved[1] >= 0 && p->reserved[1] <= 4096, "reserved[1] (segments per launch) out of range");
+    PT_CUDA(cudaSetDevice(ctx->device));
+
+    const unsigned long long total = (unsigned long long)p->width * p->height * (unsigned long long)p->spp;
+    const size_t def_cap = mode == PT_MODE_SPLIT ? (size_t)1 << 22 : (size_t)1 << 20;
+    size_t cap = p->pool_capacity > 0 ? (size_t)p->pool_capacity : def_cap;
+    if (cap > total) cap = (size_t)total;
+    cap = (cap + PT_BLOCK - 1) / PT_BLOCK * PT_BLOCK;
+    if (cap < PT_BLOCK) cap = PT_BLOCK;
+    int rc_pool = pt_ensure_pool(ctx, cap);
+    if (rc_pool) return rc_pool;
+
+    RenderConsts rc;
+    rc.cam = make_camera(cam, p->width, p->height);
+    rc.total_paths = total;
+    rc.W = p->width; rc.H = p->height;
+    rc.seed = p->seed; rc.spp_offset = (uint32_t)p->spp_offset;
+    rc.max_depth = p->max_depth; rc.shading_model = p->shading_model;
+    rc.absorptivity = p->absorptivity;
+    rc.tmin = legacy ? nextafterf(PT_EPS, 1.0f) : PT_EPS;  // legacy accepts t > eps, v2 t >= 1e-4
+    rc.pool_cap = (unsigned)cap;
+    rc.accum_sq = want_sq ? 1 : 0;
+    const unsigned long long WH = (unsigned long long)p->width * p->height;
+    rc.stride_samples = (uint32_t)(cap / WH);
+    rc.stride_pixels = (uint32_t)(cap % WH);
+    rc.sample_end = (uint32_t)(p->spp_offset + p->spp);
+
+    cudaStream_t st = ctx->stream;
+    const bool timing = (p->flags & PT_FLAG_TIMING) != 0;
+    const bool count = (p->flags & PT_FLAG_COUNTERS) != 0;
+    PT_CUDA(cudaMemsetAsync(ctx->counters, 0, CNT_TOTAL_WORDS * sizeof(unsigned long long), st));
+    PT_CUDA(cudaEventRecord(ctx->ev_a, st));
+
+    int iterations = 0, launches = 0, rcode;
+    size_t ev_idx = 0;
+    if (mode == PT_MODE_SPLIT)
+        rcode = render_split(ctx, s, rc, legacy, timing, count, (float4*)accum_dev, (float4*)accum_sq_dev, &iterations, &launches, &ev_idx);
+    else
+        rcode = render_fused(ctx, s, rc, legacy, timing, count, (float4*)accum_dev, (float4*)accum_sq_dev,
+                             p->reserved[1] > 0 ? p->reserved[1] : 32, &iterations, &launches, &ev_idx);
+    if (rcode) return rcode;
+
+    unsigned long long last[CNT_WORDS];
     PT_CUDA(cudaMemcpyAsync(last, ctx->counters, sizeof last, cudaMemcpyDeviceToHost, st));
     PT_CUDA(cudaEventRecord(ctx->ev_b, st));
     PT_CUDA(cudaStreamSynchronize(st));
@@ -356,20 +547,35 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
         cudaEventElapsedTime(&stats->ms_total, ctx->ev_a, ctx->ev_b);
         stats->iterations = iterations;
         stats->launches = launches;
-        stats->launches_extend = iterations;
-        stats->launches_shade = iterations;
-        if (timing) {
-            float e = 0, sh = 0;
-            for (size_t k = 0; k + 3 <= ev_idx; k += 3) {
-                float a = 0, b = 0;
-                cudaEventElapsedTime(&a, ctx->ev_pool[k], ctx->ev_pool[k + 1]);
-                cudaEventElapsedTime(&b, ctx->ev_pool[k + 1], ctx->ev_pool[k + 2]);
-                e += a; sh += b;
+        if (mode == PT_MODE_SPLIT) {
+            stats->launches_extend = iterations;
+            stats->launches_shade = iterations;
+            if (timing) {
+                float e = 0, sh = 0;
+                for (size_t k = 0; k + 3 <= ev_idx; k += 3) {
+                    float a = 0, b = 0;
+                    cudaEventElapsedTime(&a, ctx->ev_pool[k], ctx->ev_pool[k + 1]);
+                    cudaEventElapsedTime(&b, ctx->ev_pool[k + 1], ctx->ev_pool[k + 2]);
+                    e += a; sh += b;
+                }
+                stats->ms_extend = e;
+                stats->ms_shade = sh;
             }
-            stats->ms_extend = e;
-            stats->ms_shade = sh;
-            stats->ms_other = stats->ms_total - e - sh;
+        } else {  // fused: one kernel does both stages; its time is reported under ms_shade, launches under both
+            stats->launches_extend = 0;
+            stats->launches_shade = launches;
+            if (timing) {
+                float sh = 0;
+                for (size_t k = 0; k + 2 <= ev_idx; k += 2) {
+                    float a = 0;
+                    cudaEventElapsedTime(&a, ctx->ev_pool[k], ctx->ev_pool[k + 1]);
+                    sh += a;
+                }
+                stats->ms_shade = sh;
+            }
         }
+        if (timing) stats->ms_other = stats->ms_total - stats->ms_extend - stats->ms_shade;
+        stats->reserved[0] = mode;
     }
     return PT_OK;
 }

@@ -50,7 +50,8 @@ class Renderer:
 
     def render(self, scene: _lib.Scene, cam: _lib.PtCamera, spp: int, max_depth: int,
                shading_model: int = _lib.PT_SHADE_V2, seed: int = 1, spp_offset: int | None = None,
-               absorptivity: float = 0.25, flags: int = 0, pool_capacity: int = 0) -> _lib.PtStats:
+               absorptivity: float = 0.25, flags: int = 0, pool_capacity: int = 0, mode: int = 0,
+               segments_per_launch: int = 0) -> _lib.PtStats:
         """Adds `spp` more samples per pixel into the accumulators (progressive, legacy render(moved=False))."""
         p = _lib.PtRenderParams()
         p.width, p.height = self.width, self.height
@@ -62,6 +63,8 @@ class Renderer:
         p.absorptivity = float(absorptivity)
         p.pool_capacity = int(pool_capacity)
         p.flags = int(flags) | (_lib.PT_FLAG_ACCUM_SQ if self.accum_sq is not None else 0)
+        p.reserved[0] = int(mode)                 # 0 auto (fused), 1 split extend/shade kernels, 2 fused k_paths
+        p.reserved[1] = int(segments_per_launch)  # fused: ray segments per path slot per launch (0 = 32)
         self.ctx.set_stream(self.torch.cuda.current_stream().cuda_stream)
         st = self.ctx.render(scene, cam, p, self.accum.data_ptr(),
                              self.accum_sq.data_ptr() if self.accum_sq is not None else None)

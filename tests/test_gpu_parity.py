@@ -98,14 +98,15 @@ def test_trace_batch_edge_cases(ctx, oracle):
 
 
 # ---- images: 3 sigma of the Monte Carlo standard error ------------------------------------------
+@pytest.mark.parametrize("mode", [L.PT_MODE_FUSED, L.PT_MODE_SPLIT])
 @pytest.mark.parametrize("name,model,depth", [("6_diffuse", L.PT_SHADE_V2_DIFFUSE, 32), ("7_reflect", L.PT_SHADE_V2, 32),
                                               ("8_refract", L.PT_SHADE_V2, 50), ("9_dof", L.PT_SHADE_V2, 32),
                                               ("10_final", L.PT_SHADE_V2, 32)])
-def test_image_within_3_sigma_of_oracle(ctx, oracle, name, model, depth):
+def test_image_within_3_sigma_of_oracle(ctx, oracle, name, model, depth, mode):
     W, H, SPP = 160, 90, 256
     world, cam = scenes.SCENES[name]((W, H))
     r = L.Renderer(W, H, ctx, want_sq=True)
-    st = r.render(world.device_scene(ctx), cam.to_struct(), SPP, depth, model, seed=2)
+    st = r.render(world.device_scene(ctx), cam.to_struct(), SPP, depth, model, seed=2, mode=mode)
     s, q = r.moments()
     osum, osq, ost = oracle.render(oracle.scene_from_world(world), cam.to_struct(), W, H, SPP, depth, model, seed=2,
                                    want_sq=True)
@@ -119,6 +120,26 @@ def test_image_within_3_sigma_of_oracle(ctx, oracle, name, model, depth):
     b = L.to_uint8(oracle.postprocess(osum, 1.0 / SPP)).astype(np.float64)
     assert np.sqrt(((a - b) ** 2).mean()) < 4.0
     assert abs(mu_g.mean() / mu_o.mean() - 1.0) < 2e-3
+
+
+def test_fused_and_split_wavefronts_trace_the_same_paths(ctx):
+    """Both wavefront forms key the RNG on (pixel, sample, bounce): same paths, images equal to summation order;
+    small pools and short launches exercise regeneration, compaction and the tail."""
+    W, H = 80, 45
+    world, cam = scenes.scene_10_final((W, H))
+    sc = world.device_scene(ctx)
+    ref = None
+    for mode, cap, k in [(L.PT_MODE_SPLIT, 0, 0), (L.PT_MODE_FUSED, 0, 0), (L.PT_MODE_FUSED, 1024, 3),
+                         (L.PT_MODE_FUSED, 7000, 1), (L.PT_MODE_SPLIT, 2048, 0)]:
+        r = L.Renderer(W, H, ctx)
+        st = r.render(sc, cam.to_struct(), 24, 32, seed=5, mode=mode, pool_capacity=cap, segments_per_launch=k)
+        m = r.mean()
+        if ref is None:
+            ref, seg = m, st.segments
+        assert st.paths == W * H * 24
+        assert abs(int(st.segments) - int(seg)) <= 1e-3 * seg
+        assert np.allclose(m, ref, rtol=2e-3, atol=2e-4)
+        assert abs(m.mean() / ref.mean() - 1) < 1e-4
 
 
 def test_progressive_and_sample_split_equal_single_render(ctx):
