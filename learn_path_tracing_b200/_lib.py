@@ -139,6 +139,17 @@ def load():
     return lib
 
 
+def host_image(width: int, height: int) -> np.ndarray:
+    """float32 [W,H,3] output buffer in PINNED host memory (torch's caching host allocator), so the
+    device->host read of an image is a single DMA; falls back to pageable numpy memory without torch."""
+    try:
+        import torch
+        t = torch.empty((width, height, 3), dtype=torch.float32, pin_memory=True)
+        return t.numpy()  # keeps the pinned storage alive
+    except Exception:
+        return np.empty((width, height, 3), np.float32)
+
+
 def check(rc: int):
     if rc != 0:
         msg = load().pt_last_error()
@@ -222,13 +233,13 @@ class Context:
 
     def postprocess_host(self, accum_ptr: int, width: int, height: int, scale: float, aces: bool,
                          gamma: float) -> np.ndarray:
-        out = np.empty((width, height, 3), np.float32)
+        out = host_image(width, height)
         check(self.lib.pt_postprocess_host(self.handle, C.c_void_p(accum_ptr), width, height, scale, int(aces),
                                            gamma, _fptr(out)))
         return out
 
     def download_accum(self, accum_ptr: int, width: int, height: int) -> np.ndarray:
-        out = np.empty((width, height, 3), np.float32)
+        out = host_image(width, height)
         check(self.lib.pt_download_accum(self.handle, C.c_void_p(accum_ptr), width, height, _fptr(out)))
         return out
 

@@ -53,6 +53,7 @@ extern "C" void pt_context_destroy(PtContext* c) {
         for (int a = 0; a < 3; ++a)
             if (c->pool[q][a]) cudaFree(c->pool[q][a]);
     if (c->hits) cudaFree(c->hits);
+    if (c->scratch) cudaFree(c->scratch);
     if (c->counters) cudaFree(c->counters);
     if (c->counters_host) cudaFreeHost(c->counters_host);
     if (c->ev_a) cudaEventDestroy(c->ev_a);

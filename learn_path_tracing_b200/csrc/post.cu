@@ -49,18 +49,28 @@ extern "C" int pt_postprocess(PtContext* ctx, const void* accum_dev, int W, int 
     return PT_OK;
 }
 
+int pt_ensure_scratch(PtContext* ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes) return PT_OK;
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    PT_CUDA(cudaMalloc(&ctx->scratch, bytes));
+    ctx->scratch_bytes = bytes;
+    return PT_OK;
+}
+
 static int to_host(PtContext* ctx, const void* accum_dev, int W, int H, float scale, int aces, float gamma, int mode,
                    float* out_host) {
     PT_REQUIRE(ctx && accum_dev && out_host && W > 0 && H > 0, "bad argument");
     PT_CUDA(cudaSetDevice(ctx->device));
     const size_t n = (size_t)W * H;
-    float* d = nullptr;
-    PT_CUDA(cudaMalloc(&d, n * 3 * sizeof(float)));
+    int rc = pt_ensure_scratch(ctx, n * 3 * sizeof(float));
+    if (rc) return rc;
+    float* d = (float*)ctx->scratch;
     k_post<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const float4*)accum_dev, W, H, scale, aces, 1.0f / gamma, mode, 1, d);
-    cudaError_t e = cudaMemcpyAsync(out_host, d, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
-    PT_CUDA(e);
+    // out_host may be pinned (then this is one DMA at PCIe speed) or pageable (staged by the driver)
+    PT_CUDA(cudaMemcpyAsync(out_host, d, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CUDA(cudaStreamSynchronize(ctx->stream));
     return PT_OK;
 }
 

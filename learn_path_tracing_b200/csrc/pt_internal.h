@@ -71,6 +71,9 @@ struct PtContext {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> ev_pool;
+    // grow-only device scratch for host-layout read-backs (no cudaMalloc/cudaFree on the render path)
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
 };
 
 struct HostMesh {
@@ -129,3 +132,5 @@ int pt_lbvh_build(PtContext* ctx, const float4* d_prim_aabb, const int* d_local_
 
 // wavefront.cu
 int pt_ensure_pool(PtContext* ctx, size_t capacity);
+// post.cu
+int pt_ensure_scratch(PtContext* ctx, size_t bytes);
