@@ -146,8 +146,11 @@ int pt_scene_set_random_triangles(PtScene* s, int64_t n, uint32_t seed, float ed
 /* texture atlas in the reference's 8-bit source precision: texels[W][H] (x-major like the Taichi
  * field), each 8 bytes = albedo r,g,b, roughness, normal x,y,z, metallic (all u8, pre-gamma).  The
  * device decodes with the reference's load_texture transfer functions (15_module.py:101-104).
- * areas[ntex][4] = low.x, low.y, high.x, high.y indexed by texture id (textures_info).          */
-int pt_scene_set_texture_atlas(PtScene* s, const uint8_t* texels, int W, int H, const int32_t* areas, int ntex);
+ * areas[ntex][4] = low.x, low.y, high.x, high.y indexed by texture id (textures_info).
+ * tex_flags[ntex] (may be NULL): bit 0 = plain diffuse map without a normal map: the normal decodes to
+ * exactly (0,0,1) as load_texture's constant [0.5,0.5,1]*2-1 does (15_module.py:84,104).                */
+int pt_scene_set_texture_atlas(PtScene* s, const uint8_t* texels, int W, int H, const int32_t* areas,
+                               const int32_t* tex_flags, int ntex);
 
 /* environment map rgb[W][H][3] float (x-major), area[4]; rgb==NULL selects the v2 sky gradient
  * (backbround_color, 10_final/__main__.py:58-62).                                               */

@@ -112,7 +112,7 @@ def load():
         "pt_scene_add_mesh": (i32, [vp, vp, i32, vp, i32, vp, i32, vp, i32]),
         "pt_scene_set_triangles": (i32, [vp, vp, i64]),
         "pt_scene_set_random_triangles": (i32, [vp, i64, u32, f32]),
-        "pt_scene_set_texture_atlas": (i32, [vp, vp, i32, i32, vp, i32]),
+        "pt_scene_set_texture_atlas": (i32, [vp, vp, i32, i32, vp, vp, i32]),
         "pt_scene_set_environment": (i32, [vp, vp, i32, i32, vp]),
         "pt_scene_build": (i32, [vp]),
         "pt_scene_bvh_info": (i32, [vp, P(i64), P(i64), P(i64)]),
@@ -298,12 +298,14 @@ class Scene:
     def set_random_triangles(self, n: int, seed: int, edge_scale: float):
         check(self.lib.pt_scene_set_random_triangles(self.handle, n, seed, edge_scale))
 
-    def set_texture_atlas(self, texels: np.ndarray, areas: np.ndarray):
+    def set_texture_atlas(self, texels: np.ndarray, areas: np.ndarray, flags: np.ndarray | None = None):
         tx = np.ascontiguousarray(texels, np.uint8)
         assert tx.ndim == 3 and tx.shape[2] == 8
         ar = np.ascontiguousarray(areas, np.int32).reshape(-1, 4)
+        fl = np.zeros(ar.shape[0], np.int32) if flags is None else np.ascontiguousarray(flags, np.int32)
+        assert fl.shape[0] == ar.shape[0]
         check(self.lib.pt_scene_set_texture_atlas(self.handle, _fptr(tx, np.uint8), tx.shape[0], tx.shape[1],
-                                                  _fptr(ar, np.int32), ar.shape[0]))
+                                                  _fptr(ar, np.int32), _fptr(fl, np.int32), ar.shape[0]))
 
     def set_environment(self, rgb: np.ndarray | None, area=None):
         if rgb is None:

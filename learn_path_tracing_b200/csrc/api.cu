@@ -101,6 +101,7 @@ extern "C" void pt_scene_destroy(PtScene* s) {
     free_device(s);
     if (s->d_atlas) cudaFree(s->d_atlas);
     if (s->d_tex_areas) cudaFree(s->d_tex_areas);
+    if (s->d_tex_flags) cudaFree(s->d_tex_flags);
     if (s->d_env) cudaFree(s->d_env);
     if (s->d_lut) cudaFree(s->d_lut);
     delete s;
@@ -169,16 +170,24 @@ extern "C" int pt_scene_set_triangles(PtScene* s, const float* verts, int64_t n)
     return PT_OK;
 }
 
-extern "C" int pt_scene_set_texture_atlas(PtScene* s, const uint8_t* texels, int W, int H, const int32_t* areas, int ntex) {
+extern "C" int pt_scene_set_texture_atlas(PtScene* s, const uint8_t* texels, int W, int H, const int32_t* areas,
+                                          const int32_t* tex_flags, int ntex) {
     PT_REQUIRE(s && texels && areas && W > 0 && H > 0 && ntex > 0, "bad argument");
     PT_CUDA(cudaSetDevice(s->ctx->device));
     if (s->d_atlas) cudaFree(s->d_atlas);
     if (s->d_tex_areas) cudaFree(s->d_tex_areas);
-    s->d_atlas = nullptr; s->d_tex_areas = nullptr;
+    if (s->d_tex_flags) cudaFree(s->d_tex_flags);
+    s->d_atlas = nullptr; s->d_tex_areas = nullptr; s->d_tex_flags = nullptr;
     PT_CUDA(cudaMalloc(&s->d_atlas, (size_t)W * H * sizeof(uint2)));
     PT_CUDA(cudaMemcpy(s->d_atlas, texels, (size_t)W * H * 8, cudaMemcpyHostToDevice));
     PT_CUDA(cudaMalloc(&s->d_tex_areas, (size_t)ntex * sizeof(int4)));
     PT_CUDA(cudaMemcpy(s->d_tex_areas, areas, (size_t)ntex * sizeof(int4), cudaMemcpyHostToDevice));
+    {
+        std::vector<int32_t> fl(ntex, 0);
+        if (tex_flags) fl.assign(tex_flags, tex_flags + ntex);
+        PT_CUDA(cudaMalloc(&s->d_tex_flags, (size_t)ntex * sizeof(int)));
+        PT_CUDA(cudaMemcpy(s->d_tex_flags, fl.data(), (size_t)ntex * sizeof(int), cudaMemcpyHostToDevice));
+    }
     if (!s->d_lut) {
         // load_texture transfer functions evaluated like numpy (double) then stored as f32, 15_module.py:101-104
         float lut[768];
@@ -193,6 +202,7 @@ extern "C" int pt_scene_set_texture_atlas(PtScene* s, const uint8_t* texels, int
     }
     s->view.atlas = s->d_atlas;
     s->view.tex_areas = s->d_tex_areas;
+    s->view.tex_flags = s->d_tex_flags;
     s->view.lut = s->d_lut;
     s->view.tex_W = W; s->view.tex_H = H; s->view.ntex = ntex;
     return PT_OK;

@@ -38,6 +38,7 @@ struct SceneView {
     const int* global_prims;
     const uint2* atlas;
     const int4* tex_areas;
+    const int* tex_flags;  // bit 0: no normal map
     const float4* env;
     const float* lut;  // [3][256]: albedo^2.2, x^2, 2x-1
     int n_sph, n_tri, n_nodes, n_global;
@@ -98,6 +99,7 @@ struct PtScene {
     int* d_global = nullptr;
     uint2* d_atlas = nullptr;
     int4* d_tex_areas = nullptr;
+    int* d_tex_flags = nullptr;
     float4* d_env = nullptr;
     float* d_lut = nullptr;
     std::vector<int32_t> h_global;

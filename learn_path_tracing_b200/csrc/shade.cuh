@@ -159,6 +159,10 @@ PT_DEV Texel sample_texture(const SceneView& sv, int id, float u, float v, bool 
     Texel o;
     o.albedo = f3(0, 0, 0); o.normal = f3(0, 0, 0); o.roughness = 0.0f; o.metallic = 0.0f;
     if (id < 0 || id >= sv.ntex) return o;
+    if (__ldg(&sv.tex_flags[id]) & 1) {  // plain diffuse map: constant normal (0,0,1), 15_module.py:84,104
+        want_normal = false;
+        o.normal = f3(0.0f, 0.0f, 1.0f);
+    }
     const Taps k = bilinear_taps(__ldg(&sv.tex_areas[id]), u, v);
     texel_accum(sv, k.l, k.b, k.lb, want_normal, o);
     texel_accum(sv, k.l, k.t, k.lt, want_normal, o);

@@ -495,7 +495,7 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
     PT_CUDA(cudaSetDevice(ctx->device));
 
     const unsigned long long total = (unsigned long long)p->width * p->height * (unsigned long long)p->spp;
-    const size_t def_cap = mode == PT_MODE_SPLIT ? (size_t)1 << 22 : (size_t)1 << 20;
+    const size_t def_cap = mode == PT_MODE_SPLIT ? (size_t)1 << 22 : (size_t)1 << 21;
     size_t cap = p->pool_capacity > 0 ? (size_t)p->pool_capacity : def_cap;
     if (cap > total) cap = (size_t)total;
     cap = (cap + PT_BLOCK - 1) / PT_BLOCK * PT_BLOCK;

@@ -288,6 +288,7 @@ static inline Texel bilinear_texture(const OrcScene* sc, int id, float u, float 
                     vscale(d.normal, k.rt));
     o.roughness = ((k.lb * a.roughness + k.lt * b.roughness) + k.rb * c.roughness) + k.rt * d.roughness;
     o.metallic = ((k.lb * a.metallic + k.lt * b.metallic) + k.rb * c.metallic) + k.rt * d.metallic;
+    if (sc->tex_flags && (sc->tex_flags[id] & 1)) o.normal = v3(0.0f, 0.0f, 1.0f); /* legacy:84,104 */
     return o;
 }
 

@@ -59,6 +59,7 @@ typedef struct OrcScene {
     int32_t tex_W;
     const uint8_t* texels;
     const int32_t* tex_areas;    /* [ntex][4] */
+    const int32_t* tex_flags;    /* [ntex] bit 0: no normal map -> (0,0,1) */
     int32_t tex_H, ntex;
     /* environment, float rgb x-major [W][H][3]; NULL -> v2 sky gradient */
     const float* env;

@@ -28,7 +28,7 @@ class OrcScene(C.Structure):
     _fields_ = [("sph_cr", C.c_void_p), ("sph_mat", C.c_void_p), ("n_sph", C.c_int32), ("n_tsph", C.c_int32),
                 ("tsph_cr", C.c_void_p), ("tsph_transparency", C.c_void_p), ("tsph_tex", C.c_void_p),
                 ("meshes", C.c_void_p), ("n_mesh", C.c_int32), ("tex_W", C.c_int32), ("texels", C.c_void_p),
-                ("tex_areas", C.c_void_p), ("tex_H", C.c_int32), ("ntex", C.c_int32), ("env", C.c_void_p),
+                ("tex_areas", C.c_void_p), ("tex_flags", C.c_void_p), ("tex_H", C.c_int32), ("ntex", C.c_int32), ("env", C.c_void_p),
                 ("env_W", C.c_int32), ("env_H", C.c_int32), ("env_area", C.c_int32 * 4)]
 
 
@@ -186,11 +186,13 @@ class Scene:
         self.c.n_mesh = len(self._meshes)
         return self
 
-    def set_texture_atlas(self, texels, areas):
+    def set_texture_atlas(self, texels, areas, flags=None):
         tx = np.ascontiguousarray(texels, np.uint8)
         ar = np.ascontiguousarray(areas, np.int32).reshape(-1, 4)
+        fl = np.zeros(ar.shape[0], np.int32) if flags is None else np.ascontiguousarray(flags, np.int32)
         self.c.texels, self.c.tex_W, self.c.tex_H = self._hold(tx), tx.shape[0], tx.shape[1]
         self.c.tex_areas, self.c.ntex = self._hold(ar), ar.shape[0]
+        self.c.tex_flags = self._hold(fl)
         return self
 
     def set_environment(self, rgb, area=None):
@@ -242,3 +244,19 @@ def postprocess(accum, scale, aces=True, gamma=2.2):
 def scene_from_world(world) -> Scene:
     cr, mats = world.arrays()
     return Scene().set_spheres(cr, mats)
+
+
+def scene_from_legacy_world(world, use_stored_tree=True) -> Scene:
+    """legacy.World -> oracle scene.  With use_stored_tree the oracle walks the reference's own SAH tree from the
+    .world.npy exactly as MeshBVHTree.hit does (15_module.py:756-779); otherwise it loops over every face."""
+    sc = Scene()
+    if world.spheres:
+        sc.set_textured_spheres(*world.sphere_arrays())
+    for m in world.meshes:
+        sc.add_mesh(m["positions"], m["normals"], m["texture_coords"], m["indices"],
+                    tree=m["tree"] if use_stored_tree else None)
+    if world._atlas is not None:
+        sc.set_texture_atlas(*world._atlas)
+    if world._env is not None:
+        sc.set_environment(world._env[0], world._env[1])
+    return sc

@@ -1,0 +1,131 @@
+"""GPU parity of the legacy mesh/texture path against the oracle, which walks the
+reference's own SAH tree with the reference's triangle test and shades with the restated gen_secondary_rays."""
+import numpy as np
+import pytest
+
+import learn_path_tracing_b200 as L
+from helpers import all_triangles, cached_world, mesh_camera, synthetic_legacy_world
+
+pytestmark = pytest.mark.gpu
+
+
+def _rays_with_bounces(oracle, osc, cam, W, H, seed=3):
+    rays = oracle.generate_rays(cam.to_struct(), W, H, 0, seed)
+    ids, t = osc.trace(rays)
+    hit = ids >= 0
+    rng = np.random.default_rng(7)
+    o = rays[hit, :3] + t[hit, None] * rays[hit, 4:7]
+    d = rng.normal(size=o.shape).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    sec = np.zeros((o.shape[0], 8), np.float32)
+    sec[:, :3], sec[:, 3], sec[:, 4:7], sec[:, 7] = o + 2e-4 * d, np.nextafter(np.float32(1e-4), np.float32(1)), d, np.inf
+    rays[:, 3] = sec[0, 3] if len(sec) else rays[:, 3]   # legacy accepts t > epsilon (strict)
+    return np.concatenate([rays, sec]).astype(np.float32)
+
+
+def _check_hits(oracle, world, gid, gt, oid, ot, rays):
+    """ids equal except exact/near ties and edge grazes; miss <=> miss; t within 1e-5 relative."""
+    tris, off = all_triangles(world)
+    agree = gid == oid
+    bad = np.flatnonzero(~agree)
+    both_hit = (gid >= 0) & (oid >= 0)
+    assert np.all(np.abs(gt[agree & both_hit] - ot[agree & both_hit]) <= 1e-5 * ot[agree & both_hit] + 1e-7)
+    if len(bad):
+        g_tri = np.where(gid[bad] >= off, gid[bad] - off, -1).astype(np.int32)
+        o_tri = np.where(oid[bad] >= off, oid[bad] - off, -1).astype(np.int32)
+        _, wg = oracle.triangle_eval(tris, g_tri, rays[bad])
+        _, wo = oracle.triangle_eval(tris, o_tri, rays[bad])
+        tie = (gid[bad] >= 0) & (oid[bad] >= 0) & (np.abs(gt[bad] - ot[bad]) <= 1e-5 * np.abs(ot[bad]) + 1e-7)
+        edge = ((g_tri >= 0) & (np.abs(wg) < 2e-4)) | ((o_tri >= 0) & (np.abs(wo) < 2e-4))
+        assert np.all(tie | edge), (len(bad), int((~(tie | edge)).sum()))
+    return len(bad)
+
+
+def test_synthetic_scene_hits_match_reference_traversal(ctx, oracle):
+    world, cam = synthetic_legacy_world()
+    W, H = 192, 128
+    cam.resolution = (W, H)
+    osc = oracle.scene_from_legacy_world(world, use_stored_tree=False)
+    rays = _rays_with_bounces(oracle, osc, cam, W, H)
+    oid, ot = osc.trace(rays)
+    gid, gt = world.hit(rays, ctx)
+    n_bad = _check_hits(oracle, world, gid, gt, oid, ot, rays)
+    assert n_bad <= 5e-4 * len(rays) + 2
+    sph = oid < 2
+    assert sph.any() and np.array_equal(gt[sph & (gid == oid)], ot[sph & (gid == oid)])  # spheres: bit-exact t
+    n_nodes, n_prims, n_global = world.device_scene(ctx).bvh_info()
+    assert n_prims == 2 + 2 * 14 * 14 + 2 and n_global >= 2  # the +-50 ground triangles stay out of the LBVH
+
+
+@pytest.mark.parametrize("name", ["demo", "yoimiya_ground_small", "zhongli_small"])
+def test_cached_scene_hits_match_reference_traversal(ctx, oracle, name):
+    world = cached_world(name)
+    if world is None:
+        pytest.skip("scene cache not built (tools/prepare_assets.py needs the reference checkout)")
+    W, H = 240, 160
+    cam = mesh_camera((W, H))
+    if name == "demo":
+        cam.set_position(L.legacy.Vec3f([3, 2, -6]))
+        cam.look_at(L.legacy.Vec3f([0, 0, 0]))
+    osc = oracle.scene_from_legacy_world(world, use_stored_tree=True)   # the reference's own traversal + tree
+    rays = _rays_with_bounces(oracle, osc, cam, W, H)
+    oid, ot = osc.trace(rays)
+    gid, gt = world.hit(rays, ctx)
+    assert (oid >= 0).mean() > 0.05
+    n_bad = _check_hits(oracle, world, gid, gt, oid, ot, rays)
+    assert n_bad <= 0.02 * len(rays)  # duplicated / double-sided faces of the models tie exactly
+
+
+def _image_parity(ctx, oracle, world, cam, W, H, spp, depth, absorptivity, use_tree):
+    r = L.Renderer(W, H, ctx, want_sq=True)
+    st = r.render(world.device_scene(ctx), cam.to_struct(), spp, depth, L.PT_SHADE_LEGACY, seed=4,
+                  absorptivity=absorptivity)
+    s, q = r.moments()
+    osum, osq, ost = oracle.render(oracle.scene_from_legacy_world(world, use_stored_tree=use_tree), cam.to_struct(), W, H,
+                                   spp, depth, L.PT_SHADE_LEGACY, seed=4, absorptivity=absorptivity, want_sq=True)
+    mu_g, mu_o = s / spp, osum / spp
+    var = (np.maximum(q / spp - mu_g**2, 0) + np.maximum(osq / spp - mu_o**2, 0)) / spp
+    z = np.abs(mu_g - mu_o) / np.sqrt(var + 1e-10)
+    assert st.paths == ost.paths
+    assert abs(st.segments / ost.segments - 1.0) < 0.01, (st.segments, ost.segments)
+    assert (z > 3).mean() < 0.01, float((z > 3).mean())
+    assert z.max() < 8.0, float(z.max())
+    assert abs(mu_g.mean() / mu_o.mean() - 1.0) < 3e-3
+    a = L.to_uint8(r.image(aces=False)).astype(np.float64)
+    b = L.to_uint8(oracle.postprocess(osum, 1.0 / spp, aces=False)).astype(np.float64)
+    return float(np.sqrt(((a - b) ** 2).mean()))
+
+
+@pytest.mark.parametrize("absorptivity", [0.25, 0.5])
+def test_synthetic_scene_image_within_3_sigma(ctx, oracle, absorptivity):
+    world, cam = synthetic_legacy_world()
+    rmse = _image_parity(ctx, oracle, world, cam, 96, 64, 192, 16, absorptivity, use_tree=False)
+    assert rmse < 6.0
+
+
+@pytest.mark.parametrize("name,spp", [("demo", 128), ("yoimiya_ground_small", 64), ("zhongli_small", 64)])
+def test_cached_scene_image_within_3_sigma(ctx, oracle, name, spp):
+    world = cached_world(name)
+    if world is None:
+        pytest.skip("scene cache not built")
+    W, H = 120, 80
+    cam = mesh_camera((W, H))
+    if name == "demo":
+        cam.set_position(L.legacy.Vec3f([3, 2, -6]))
+        cam.look_at(L.legacy.Vec3f([0, 0, 0]))
+    rmse = _image_parity(ctx, oracle, world, cam, W, H, spp, 32, 0.25, use_tree=True)
+    assert rmse < 8.0
+
+
+def test_legacy_renderer_progressive(ctx):
+    """render(moved=False) keeps accumulating (15_module.py:1022-1036); frame = (image / total spp)^(1/2.2)."""
+    world, cam = synthetic_legacy_world()
+    lr = L.legacy.LegacyRenderer(world, cam, spp=8, propagate_limit=8, ctx=ctx)
+    f1 = lr.render(moved=True)
+    f2 = lr.render(moved=False)
+    assert lr.total_spp == 16 and f1.shape == (96, 64, 3)
+    one = L.legacy.LegacyRenderer(world, cam, spp=16, propagate_limit=8, ctx=ctx).render()
+    assert np.allclose(f2, one, rtol=2e-3, atol=2e-3)
+    assert not np.allclose(f1, f2)
+    f3 = lr.render(moved=True)
+    assert lr.total_spp == 8 and np.allclose(f3, f1, rtol=2e-3, atol=2e-3)
