@@ -361,6 +361,27 @@ class Camera:
         return ctx.generate_rays(self.to_struct(), self.resolution[0], self.resolution[1], int(sample), int(seed))
 
 
+def reference_visit_order(tree, n_faces) -> np.ndarray:
+    """Order in which MeshBVHTree.hit (15_module.py:756-779) reaches the faces: it pushes left then right, so the
+    RIGHT subtree is popped first; faces inside a leaf run in CSR order.  The reference keeps the first face it
+    meets among exactly equal t (strict <), so this order decides ties between duplicated / double-sided faces."""
+    if tree is None:
+        return np.arange(n_faces, dtype=np.int64)
+    left, right, data, cut = tree["left"], tree["right"], tree["data"], tree["leaf_cut"]
+    order = []
+    stack = [0]
+    while stack:
+        cur = stack.pop()
+        if data[cur] >= 0:
+            order.extend(range(int(cut[data[cur]]), int(cut[data[cur] + 1])))
+        else:
+            stack.append(int(left[cur]))
+            stack.append(int(right[cur]))
+    order = np.asarray(order, np.int64)
+    assert len(order) == n_faces and len(np.unique(order)) == n_faces
+    return order
+
+
 # ---- world -------------------------------------------------------------------------------------------
 class World:
     """15_module.py:782-848."""
@@ -497,8 +518,15 @@ class World:
             sc = _lib.Scene(ctx)
             if self.spheres:
                 sc.set_textured_spheres(*self.sphere_arrays())
+            perm, base = [], 0
             for m in self.meshes:
-                sc.add_mesh(m["positions"], m["normals"], m["texture_coords"], m["indices"])
+                # device primitive order = the reference traversal's visitation order, so that "lowest id wins an
+                # exact tie" (extend.cuh) picks the face the reference would have kept
+                order = reference_visit_order(m.get("tree"), len(m["indices"]))
+                sc.add_mesh(m["positions"], m["normals"], m["texture_coords"], m["indices"][order])
+                perm.append(base + order)
+                base += len(order)
+            self._tri_perm = np.concatenate(perm) if perm else np.zeros(0, np.int64)
             if self._atlas is None:
                 raise _lib.PtError("legacy World has no texture atlas: call build()/load_textures() or set_atlas()")
             sc.set_texture_atlas(*self._atlas)
@@ -515,6 +543,10 @@ class World:
         from .render import default_context
         ctx = ctx or default_context()
         ids, t, _ = ctx.trace_batch(self.device_scene(ctx), rays)
+        n_sph = len(self.spheres)
+        tri = ids >= n_sph
+        ids = ids.copy()
+        ids[tri] = n_sph + self._tri_perm[ids[tri] - n_sph]  # device order -> the caller's face order
         return ids, t
 
 

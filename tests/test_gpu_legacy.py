@@ -23,21 +23,44 @@ def _rays_with_bounces(oracle, osc, cam, W, H, seed=3):
     return np.concatenate([rays, sec]).astype(np.float32)
 
 
-def _check_hits(oracle, world, gid, gt, oid, ot, rays):
-    """ids equal except exact/near ties and edge grazes; miss <=> miss; t within 1e-5 relative."""
+def _tolerance(tris, tri_ids, rays, t):
+    """|dt| bound for one (ray, triangle) pair: the contract's 1e-5 relative, plus the unavoidable rounding of f32
+    coordinates (a few ulps of the scene scale) amplified by 1/|d.N| when the ray grazes the triangle's plane."""
+    T = tris[np.maximum(tri_ids, 0)]
+    n = np.cross(T[:, 3:6] - T[:, 0:3], T[:, 6:9] - T[:, 0:3])
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    dn = np.abs((rays[:, 4:7] * n).sum(1))
+    scale = np.maximum(np.abs(rays[:, :3]).max(1), np.abs(T).max(1))
+    return 1e-5 * np.abs(t) + 16 * 1.2e-7 * scale / np.maximum(dn, 1e-12)
+
+
+def _check_hits(oracle, world, gid, gt, oid, ot, rays, n_primary):
+    """ids equal except ties and edge grazes; miss <=> miss up to grazing self-hits; primary
+    (camera) rays: t within 1e-5 relative; secondary rays: 1e-5 relative + conditioning-aware rounding bound."""
     tris, off = all_triangles(world)
     agree = gid == oid
+    hit = agree & (gid >= 0)
+    prim = np.arange(len(rays)) < n_primary
+    assert np.all(np.abs(gt[hit & prim] - ot[hit & prim]) <= 1e-5 * ot[hit & prim])
+    th = hit & (gid >= off)
+    tol = _tolerance(tris, (gid[th] - off).astype(np.int64), rays[th], ot[th])
+    assert np.all(np.abs(gt[th] - ot[th]) <= tol)
     bad = np.flatnonzero(~agree)
-    both_hit = (gid >= 0) & (oid >= 0)
-    assert np.all(np.abs(gt[agree & both_hit] - ot[agree & both_hit]) <= 1e-5 * ot[agree & both_hit] + 1e-7)
     if len(bad):
         g_tri = np.where(gid[bad] >= off, gid[bad] - off, -1).astype(np.int32)
         o_tri = np.where(oid[bad] >= off, oid[bad] - off, -1).astype(np.int32)
-        _, wg = oracle.triangle_eval(tris, g_tri, rays[bad])
-        _, wo = oracle.triangle_eval(tris, o_tri, rays[bad])
-        tie = (gid[bad] >= 0) & (oid[bad] >= 0) & (np.abs(gt[bad] - ot[bad]) <= 1e-5 * np.abs(ot[bad]) + 1e-7)
+        tg, wg = oracle.triangle_eval(tris, g_tri, rays[bad])   # reference plane-t and min barycentric of each side's triangle
+        to, wo = oracle.triangle_eval(tris, o_tri, rays[bad])
+        tol_g = np.where(g_tri >= 0, _tolerance(tris, g_tri, rays[bad], gt[bad]), 1e-6)
+        tol_o = np.where(o_tri >= 0, _tolerance(tris, o_tri, rays[bad], ot[bad]), 1e-6)
+        both = (gid[bad] >= 0) & (oid[bad] >= 0)
+        tie = both & (np.abs(gt[bad] - ot[bad]) <= tol_g + tol_o)
         edge = ((g_tri >= 0) & (np.abs(wg) < 2e-4)) | ((o_tri >= 0) & (np.abs(wo) < 2e-4))
-        assert np.all(tie | edge), (len(bad), int((~(tie | edge)).sum()))
+        # acceptance flips at t ~ epsilon: one side sees the (grazing) surface just above 1e-4, the other just below
+        eps_flip = ((g_tri >= 0) & (np.abs(tg - 1e-4) <= tol_g + np.abs(gt[bad] - tg))) | \
+                   ((o_tri >= 0) & (np.abs(to - 1e-4) <= tol_o))
+        ok = tie | edge | eps_flip
+        assert np.all(ok), (len(bad), int((~ok).sum()))
     return len(bad)
 
 
@@ -49,7 +72,7 @@ def test_synthetic_scene_hits_match_reference_traversal(ctx, oracle):
     rays = _rays_with_bounces(oracle, osc, cam, W, H)
     oid, ot = osc.trace(rays)
     gid, gt = world.hit(rays, ctx)
-    n_bad = _check_hits(oracle, world, gid, gt, oid, ot, rays)
+    n_bad = _check_hits(oracle, world, gid, gt, oid, ot, rays, W * H)
     assert n_bad <= 5e-4 * len(rays) + 2
     sph = oid < 2
     assert sph.any() and np.array_equal(gt[sph & (gid == oid)], ot[sph & (gid == oid)])  # spheres: bit-exact t
@@ -72,8 +95,10 @@ def test_cached_scene_hits_match_reference_traversal(ctx, oracle, name):
     oid, ot = osc.trace(rays)
     gid, gt = world.hit(rays, ctx)
     assert (oid >= 0).mean() > 0.05
-    n_bad = _check_hits(oracle, world, gid, gt, oid, ot, rays)
-    assert n_bad <= 0.02 * len(rays)  # duplicated / double-sided faces of the models tie exactly
+    n_bad = _check_hits(oracle, world, gid, gt, oid, ot, rays, W * H)
+    # exact ties between duplicated faces resolve like the reference (device order = its visitation order): what is
+    # left are near-ties between twin faces whose t differs in the last ulps
+    assert n_bad <= 2e-3 * len(rays), n_bad
 
 
 def _image_parity(ctx, oracle, world, cam, W, H, spp, depth, absorptivity, use_tree):
@@ -125,7 +150,9 @@ def test_legacy_renderer_progressive(ctx):
     f2 = lr.render(moved=False)
     assert lr.total_spp == 16 and f1.shape == (96, 64, 3)
     one = L.legacy.LegacyRenderer(world, cam, spp=16, propagate_limit=8, ctx=ctx).render()
-    assert np.allclose(f2, one, rtol=2e-3, atol=2e-3)
+    # bilinear's extrapolating taps (15_module.py:245-250) can give a negative environment value -> NaN after the
+    # gamma power, in the reference as here
+    assert np.allclose(f2, one, rtol=2e-3, atol=2e-3, equal_nan=True) and np.isnan(f2).mean() < 0.02
     assert not np.allclose(f1, f2)
     f3 = lr.render(moved=True)
-    assert lr.total_spp == 8 and np.allclose(f3, f1, rtol=2e-3, atol=2e-3)
+    assert lr.total_spp == 8 and np.allclose(f3, f1, rtol=2e-3, atol=2e-3, equal_nan=True)
