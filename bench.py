@@ -27,11 +27,17 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
-    # name: (scene, W, H, spp, depth, shading model name)
-    "8_refract_1080p": ("8_refract", 1920, 1080, 256, 50),
-    "10_final_720p": ("10_final", 1280, 720, 256, 32),   # configs[0] scene at reduced spp (8192 in the script)
+    # name: (scene, W, H, spp, depth)
+    "8_refract_1080p": ("8_refract", 1920, 1080, 256, 50),      # BASELINE configs[1]: the headline workload
+    "10_final_720p": ("10_final", 1280, 720, 256, 32),          # configs[0] scene at reduced spp (8192 in the script)
     "9_dof_720p": ("9_dof", 1280, 720, 256, 32),
+    # legacy mesh scenes (need scenes_cache/*.npz from tools/prepare_assets.py): configs[2] and configs[3]
+    "yoimiya_1080p": ("cache:yoimiya_ground_full", 1920, 1080, 512, 32),
+    "zhongli_4k": ("cache:zhongli_full", 3840, 2160, 64, 32),   # configs[3] at reduced spp (4096 in the config)
 }
+# BASELINE configs[4]: synthetic 10M-triangle scene, 64Mi-ray intersection-only batch
+INTERSECT = {"intersect_10m": (10_000_000, 64 * 2**20, 12345, 54321, 0.004),
+             "intersect_1m": (1_000_000, 8 * 2**20, 12345, 54321, 0.0086)}
 # algorithmic HBM bytes: per ray segment / per path
 B_EXTEND_SEG = 48    # read o|d 32 B, write hit 16 B
 B_SHADE_SEG = 112    # read o|d 32 + throughput 16 + hit 16, write compacted successor 48
@@ -92,24 +98,42 @@ class ClockSampler(threading.Thread):
 
 
 def build_workload(name):
+    """-> (world, camera, W, H, spp, depth, shading model, oracle scene builder)"""
+    import learn_path_tracing_b200 as L
     from learn_path_tracing_b200 import scenes
     scene, W, H, spp, depth = WORKLOADS[name]
+    if scene.startswith("cache:"):
+        from learn_path_tracing_b200 import legacy, scene_cache
+        path = os.path.join(ROOT, "scenes_cache", scene[6:] + ".npz")
+        if not os.path.exists(path):
+            raise SystemExit(f"bench.py: {path} missing (python tools/prepare_assets.py needs the reference checkout)")
+        world = scene_cache.load_cache(path)
+        cam = legacy.Camera((W, H))       # 15_module.py:1068-1072
+        cam.set_fov(30)
+        cam.set_position(legacy.Vec3f([0, 8, -30]))
+        cam.look_at(legacy.Vec3f([0, 8, 0]))
+        return world, cam, W, H, spp, depth, L.PT_SHADE_LEGACY
     world, cam = scenes.SCENES[scene]((W, H))
-    return world, cam, W, H, spp, depth
+    return world, cam, W, H, spp, depth, L.PT_SHADE_V2
 
 
-def cpu_baseline_run(world, cam, W, H, depth, target_seconds, threads=0):
-    """Times the oracle (kind 'port': the reference's algorithm in C + OpenMP) on a bounded sample."""
+def oracle_scene(world, model):
     from oracle import ptoracle as O
     import learn_path_tracing_b200 as L
-    sc = O.scene_from_world(world)
+    return O.scene_from_legacy_world(world) if model == L.PT_SHADE_LEGACY else O.scene_from_world(world)
+
+
+def cpu_baseline_run(world, cam, W, H, depth, target_seconds, threads=0, model=0):
+    """Times the oracle (kind 'port': the reference's algorithm in C + OpenMP) on a bounded sample."""
+    from oracle import ptoracle as O
+    sc = oracle_scene(world, model)
     cs = cam.to_struct()
     t0 = time.perf_counter()
-    O.render(sc, cs, W, H, 1, depth, L.PT_SHADE_V2, seed=1, threads=threads)
+    O.render(sc, cs, W, H, 1, depth, model, seed=1, threads=threads)
     t1 = time.perf_counter() - t0
     spp = int(max(1, min(64, target_seconds / max(t1, 1e-3))))
     t0 = time.perf_counter()
-    _, _, st = O.render(sc, cs, W, H, spp, depth, L.PT_SHADE_V2, seed=1, threads=threads)
+    _, _, st = O.render(sc, cs, W, H, spp, depth, model, seed=1, threads=threads)
     dt = time.perf_counter() - t0
     cores = O.num_threads() if threads <= 0 else threads
     return {"mpaths": st.paths / dt / 1e6, "mrays": st.segments / dt / 1e6, "seconds": dt, "spp": spp, "cores": cores}
@@ -119,11 +143,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    world, cam, W, H, spp, depth = build_workload(args.workload)
+    world, cam, W, H, spp, depth, model = build_workload(args.workload)
     per_step = 8.0
     vals = []
     for i in range(args.warmup + args.steps):
-        r = cpu_baseline_run(world, cam, W, H, depth, per_step if i else 2.0)
+        r = cpu_baseline_run(world, cam, W, H, depth, per_step if i else 2.0, model=model)
         if i >= args.warmup:
             vals.append(r)
     v = float(np.mean([r["mpaths"] for r in vals]))
@@ -157,7 +181,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world_size > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    world, cam, W, H, spp, depth = build_workload(args.workload)
+    world, cam, W, H, spp, depth, model = build_workload(args.workload)
     ctx = L.default_context()
     scene = world.device_scene(ctx)
     cs = cam.to_struct()
@@ -168,7 +192,7 @@ def run_ours(args):
 
     def step(flags=0):
         r.clear()
-        st = r.render(scene, cs, spp, depth, L.PT_SHADE_V2, seed=1, spp_offset=rank * spp, flags=flags, mode=args.mode,
+        st = r.render(scene, cs, spp, depth, model, seed=1, spp_offset=rank * spp, flags=flags, mode=args.mode,
                       pool_capacity=args.pool, segments_per_launch=args.k)
         if world_size > 1:
             dist.reduce(r.accum, dst=0, op=dist.ReduceOp.SUM)
@@ -206,15 +230,23 @@ def run_ours(args):
     # ---- end-to-end through the public API with host buffers (scene upload + build + render + D2H image)
     e2e = None
     if True:
-        cr, mats = world.arrays()
-        h2d = cr.nbytes + mats.nbytes + 64 + 64
+        legacy_scene = model == L.PT_SHADE_LEGACY
+        if legacy_scene:
+            h2d = sum(m["positions"].nbytes + m["normals"].nbytes + m["texture_coords"].nbytes + m["indices"].nbytes
+                      for m in world.meshes) + world._atlas[0].nbytes + (world._env[0].nbytes if world._env else 0) + 128
+        else:
+            cr, mats = world.arrays()
+            h2d = cr.nbytes + mats.nbytes + 64 + 64
         d2h = W * H * 3 * 4
         e_times = []
         for i in range(2 + min(args.steps, 3)):
             world._scene = None  # force re-upload + rebuild: the scene starts on the host every step
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            if world_size > 1:
+            if legacy_scene:
+                lr = L.legacy.LegacyRenderer(world, cam, spp=spp, propagate_limit=depth, ctx=ctx)
+                img = lr.render(moved=True)
+            elif world_size > 1:
                 img = L.render_distributed(world, cam, spp=spp * world_size, propagate_limit=depth, seed=1, ctx=ctx)
             else:
                 img = L.render(world, cam, spp=spp, propagate_limit=depth, seed=1, ctx=ctx)
@@ -253,7 +285,7 @@ def run_ours(args):
             fp32_peak = ctx.measure_fp32_peak()
         except Exception:
             fp32_peak = None
-        cpu = cpu_baseline_run(world, cam, W, H, depth, 0.5 if args.no_cpu else 12.0)
+        cpu = cpu_baseline_run(world, cam, W, H, depth, 0.5 if args.no_cpu else 12.0, model=model)
         line = {
             "metric": "Mpaths/s", "value": paths_total / (t_max * 1e-3) / 1e6, "unit": "Mpaths/s",
             "n_gpus": world_size, "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": t_max / K,
@@ -275,8 +307,112 @@ def run_ours(args):
             "fp32_peak_tflops_measured": fp32_peak,
             "cpu_baseline": {"value": cpu["mpaths"], "unit": "Mpaths/s", "cores": cpu["cores"], "kind": "port",
                              "sample": f"{W}x{H}, {cpu['spp']} spp, depth {depth}, {cpu['seconds']:.1f} s of OpenMP C "
-                                       f"oracle (reference algorithm: brute-force sphere loop per bounce)",
+                                       f"oracle (reference algorithm: " + ("unpruned stack walk of the stored SAH tree, "
+                                       "texture fetch per candidate" if model == L.PT_SHADE_LEGACY else
+                                       "brute-force sphere loop per bounce") + ")",
                              "mrays_per_s": cpu["mrays"]},
+        }
+        print(json.dumps(line), flush=True)
+    if world_size > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_intersect(args):
+    """BASELINE configs[4]: fixed ray batch against an LBVH over random triangles, intersection only.
+    Rays and triangles are generated on the device by counter-based generators (bit-identical to the oracle's);
+    N > 1 shards the ray batch by ranges, no collective."""
+    import torch
+    import torch.distributed as dist
+    import learn_path_tracing_b200 as L
+    from oracle import ptoracle as O
+
+    n_tri, n_rays, seed_t, seed_r, edge = INTERSECT[args.workload]
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = L.default_context()
+    sc = L.Scene(ctx)
+    t0 = time.perf_counter()
+    sc.set_random_triangles(n_tri, seed_t, edge)
+    sc.build()
+    build_s = time.perf_counter() - t0
+    n_local = n_rays // world_size
+    rays = torch.empty((2 * n_rays, 4), dtype=torch.float32, device="cuda")
+    ctx.random_rays_device(rays.data_ptr(), n_rays, seed_r)
+    my = rays[2 * rank * n_local: 2 * (rank + 1) * n_local]
+    hits = torch.empty((n_local, 4), dtype=torch.float32, device="cuda")
+    flush = torch.empty(int(2 * L2_BYTES) // 4, dtype=torch.float32, device="cuda")
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(max(args.warmup, 3)):
+        ctx.trace_batch_device(sc, my.data_ptr(), n_local, hits.data_ptr())
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    times = []
+    for _ in range(args.steps):
+        flush.fill_(1.0)
+        torch.cuda.synchronize()
+        if world_size > 1:
+            dist.barrier()
+        ev0.record()
+        ctx.trace_batch_device(sc, my.data_ptr(), n_local, hits.data_ptr())
+        ev1.record()
+        torch.cuda.synchronize()
+        times.append(ev0.elapsed_time(ev1))
+    clocks = sampler.result()
+    t_local = float(sum(times))
+    t_max = t_local
+    if world_size > 1:
+        tt = torch.tensor([t_local], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_max = float(tt.item())
+    st = ctx.trace_batch_device(sc, my.data_ptr(), n_local, hits.data_ptr(), L.PT_FLAG_COUNTERS)
+    # e2e: host ray buffer in, host ids/t out (pt_trace_batch), on a bounded slice
+    n_e = min(n_local, 4 * 2**20)
+    rays_h = my[:2 * n_e].cpu().numpy().reshape(n_e, 8)
+    te = []
+    for i in range(3):
+        t0 = time.perf_counter()
+        ids_h, t_h, _ = ctx.trace_batch(sc, rays_h)
+        te.append(time.perf_counter() - t0)
+    if rank == 0:
+        peak, peak_kind = measured_peaks()
+        K = args.steps
+        nodes_per_ray = st.nodes_visited / n_local
+        tris_per_ray = st.prims_tested / n_local
+        bytes_per_ray = 32 + 8 + 64 * nodes_per_ray + 48 * tris_per_ray
+        achieved = bytes_per_ray * n_local * K / (t_local * 1e-3) / 1e9
+        # CPU baseline: the oracle walking the SAME LBVH with the reference triangle test, bounded ray sample
+        n_c = 2**18
+        nodes, _ = sc.bvh_download()
+        tris = O.random_triangles(n_tri, seed_t, edge)
+        t0 = time.perf_counter()
+        oid, ot, _ = O.trace_bvh2(nodes, tris, rays_h[:n_c])
+        cpu_s = time.perf_counter() - t0
+        gid = ids_h[:n_c]
+        agree = float((gid == oid).mean())
+        line = {
+            "metric": "Mrays/s", "value": n_local * world_size * K / (t_max * 1e-3) / 1e6, "unit": "Mrays/s",
+            "n_gpus": world_size, "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": t_max / K,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "triangles": n_tri, "rays": n_rays, "edge_scale": edge,
+                       "parallelism": f"ray ranges x{world_size}, no collective", "l2": "flushed between timed steps",
+                       "lbvh_build_s": build_s},
+            "hit_fraction": float((ids_h >= 0).mean()), "ids_equal_to_oracle": agree,
+            "e2e": {"value": n_e / min(te) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(n_e * 32),
+                    "d2h_bytes_per_step": int(n_e * 16)},
+            "gpu_launches": K, "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                         "algorithmic_bytes": f"32 + 8 + 64*{nodes_per_ray:.1f} nodes + 48*{tris_per_ray:.2f} triangles "
+                                              f"= {bytes_per_ray:.0f} B/ray (SURVEY 8d; counts from a counter-instrumented run)",
+                         "compulsory_40B_per_ray": {"achieved": 40.0 * n_local * K / (t_local * 1e-3) / 1e9}},
+            "cpu_baseline": {"value": n_c / cpu_s / 1e6, "unit": "Mrays/s", "cores": O.num_threads(), "kind": "port",
+                             "sample": f"{n_c} rays of the same batch, oracle walking the same LBVH with the reference "
+                                       f"triangle test, {cpu_s:.1f} s"},
         }
         print(json.dumps(line), flush=True)
     if world_size > 1:
@@ -290,13 +426,17 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="8_refract_1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="8_refract_1080p", choices=sorted(WORKLOADS) + sorted(INTERSECT))
     ap.add_argument("--mode", type=int, default=0, help="wavefront mode: 0 auto (fused), 1 split kernels, 2 fused")
     ap.add_argument("--pool", type=int, default=0, help="path-pool slots (0 = library default)")
     ap.add_argument("--k", type=int, default=0, help="fused mode: segments per launch (0 = default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload in INTERSECT:
+        if args.impl == "reference":
+            raise SystemExit("--impl reference: use a render workload (the intersect line carries its own cpu_baseline)")
+        run_intersect(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
