@@ -193,7 +193,7 @@ def run_ours(args):
     def step(flags=0):
         r.clear()
         st = r.render(scene, cs, spp, depth, model, seed=1, spp_offset=rank * spp, flags=flags, mode=args.mode,
-                      pool_capacity=args.pool, segments_per_launch=args.k)
+                      pool_capacity=args.pool, segments_per_launch=args.k, shade_min=args.shade_min, serve_min=args.serve_min)
         if world_size > 1:
             dist.reduce(r.accum, dst=0, op=dist.ReduceOp.SUM)
         return st
@@ -348,7 +348,7 @@ def run_intersect(args):
     flush = torch.empty(int(2 * L2_BYTES) // 4, dtype=torch.float32, device="cuda")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(max(args.warmup, 3)):
-        ctx.trace_batch_device(sc, my.data_ptr(), n_local, hits.data_ptr())
+        ctx.trace_batch_device(sc, my.data_ptr(), n_local, hits.data_ptr(), args.trace_flags)
     sampler = ClockSampler(local_rank)
     sampler.start()
     times = []
@@ -358,7 +358,7 @@ def run_intersect(args):
         if world_size > 1:
             dist.barrier()
         ev0.record()
-        ctx.trace_batch_device(sc, my.data_ptr(), n_local, hits.data_ptr())
+        ctx.trace_batch_device(sc, my.data_ptr(), n_local, hits.data_ptr(), args.trace_flags)
         ev1.record()
         torch.cuda.synchronize()
         times.append(ev0.elapsed_time(ev1))
@@ -369,7 +369,7 @@ def run_intersect(args):
         tt = torch.tensor([t_local], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_max = float(tt.item())
-    st = ctx.trace_batch_device(sc, my.data_ptr(), n_local, hits.data_ptr(), L.PT_FLAG_COUNTERS)
+    st = ctx.trace_batch_device(sc, my.data_ptr(), n_local, hits.data_ptr(), L.PT_FLAG_COUNTERS | args.trace_flags)
     # e2e: host ray buffer in, host ids/t out (pt_trace_batch), on a bounded slice
     n_e = min(n_local, 4 * 2**20)
     rays_h = my[:2 * n_e].cpu().numpy().reshape(n_e, 8)
@@ -430,6 +430,9 @@ def main():
     ap.add_argument("--mode", type=int, default=0, help="wavefront mode: 0 auto (fused), 1 split kernels, 2 fused")
     ap.add_argument("--pool", type=int, default=0, help="path-pool slots (0 = library default)")
     ap.add_argument("--k", type=int, default=0, help="fused mode: segments per launch (0 = default)")
+    ap.add_argument("--shade-min", type=int, default=0, help="persistent mode: waiting lanes that trigger shading (0 = default)")
+    ap.add_argument("--serve-min", type=int, default=0, help="persistent mode: waiting lanes that trigger a service (0 = default)")
+    ap.add_argument("--trace-flags", type=int, default=0, help="intersect workloads: PT_FLAG_* for pt_trace_batch_device")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.workload in INTERSECT:

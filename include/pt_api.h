@@ -58,6 +58,12 @@ extern "C" {
 #define PT_FLAG_ACCUM_SQ 1      /* also accumulate per-pixel sum of squares (needs accum_sq != NULL)   */
 #define PT_FLAG_TIMING 2        /* record CUDA events around every kernel launch (fills PtStats.ms_*)  */
 #define PT_FLAG_COUNTERS 4      /* count BVH nodes visited / primitives tested (slower)                */
+/* pt_trace_batch_device flags */
+#define PT_FLAG_NO_SORT 8       /* keep the batch order (default: batches >= 65536 rays are traced in an
+                                   entry-point/direction Morton order; results always land in batch order) */
+#define PT_FLAG_TRACE_SIMPLE 16 /* one ray per thread (k_trace) instead of the persistent while-while warps */
+/* bits 8-13 of the trace flags: lanes that must wait before a warp services them (0 = default 8);
+   bits 14-19: finished lanes that trigger result write-back + refill (0 = default 8) */
 
 typedef struct PtContext PtContext;
 typedef struct PtScene PtScene;
@@ -94,8 +100,11 @@ typedef struct PtRenderParams {
     float absorptivity;     /* legacy only: 0.25 (15_module.py:893,950) or 0.5 (14_mesh.py:833,889) */
     int32_t pool_capacity;  /* path-pool slots; 0 = library default                                 */
     int32_t flags;          /* PT_FLAG_*                                                            */
-    int32_t reserved[6];    /* [0] wavefront mode: 0 auto, 1 split (k_extend + k_shade per bounce), 2 fused (k_paths)
-                               [1] fused mode: ray segments per path slot per launch (0 = default 32)        */
+    int32_t reserved[6];    /* [0] wavefront mode: 0 auto (3 when the scene has a BVH, else 2), 1 split (k_extend +
+                                   k_shade per bounce), 2 fused K-step (k_paths), 3 persistent while-while (k_paths_persist)
+                               [1] fused mode: ray segments per path slot per launch (0 = default 32)
+                               [2] persistent mode: finished lanes that trigger shading + refill (0 = default 12)
+                               [3] persistent mode: waiting lanes that trigger a service (leaf tests) (0 = default 8)  */
 } PtRenderParams; /* 64 bytes */
 
 typedef struct PtStats {

@@ -54,6 +54,7 @@ extern "C" void pt_context_destroy(PtContext* c) {
             if (c->pool[q][a]) cudaFree(c->pool[q][a]);
     if (c->hits) cudaFree(c->hits);
     if (c->scratch) cudaFree(c->scratch);
+    if (c->sort_scratch) cudaFree(c->sort_scratch);
     if (c->counters) cudaFree(c->counters);
     if (c->counters_host) cudaFreeHost(c->counters_host);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
@@ -488,6 +489,16 @@ extern "C" int pt_scene_build(PtScene* s) {
         if (d_ids) cudaFree(d_ids);
         PT_CUDA(e);
         if (rc) return rc;
+    }
+    if (root != PT_NO_BVH && s->n_nodes > 0) {  // root box = union of node 0's two child boxes
+        float n0[16];
+        PT_CUDA(cudaMemcpy(n0, s->d_nodes, sizeof n0, cudaMemcpyDeviceToHost));
+        const float lo0[3] = {n0[0], n0[1], n0[2]}, hi0[3] = {n0[3], n0[4], n0[5]};
+        const float lo1[3] = {n0[6], n0[7], n0[8]}, hi1[3] = {n0[9], n0[10], n0[11]};
+        for (int c = 0; c < 3; ++c) {
+            s->bounds_lo[c] = fminf(lo0[c], lo1[c]);
+            s->bounds_hi[c] = fmaxf(hi0[c], hi1[c]);
+        }
     }
     SceneView& v = s->view;
     v.sph_cr = s->d_sph_cr; v.sph_aux = s->d_sph_aux; v.sph_mat = s->d_sph_mat;

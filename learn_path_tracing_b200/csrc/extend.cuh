@@ -141,3 +141,109 @@ PT_DEV Hit closest_hit(const SceneView& sv, float3 o, float3 d, float tmin, floa
     }
     return h;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Resumable traversal for the persistent kernels (persist.cu).  Same result as closest_hit() — closest
+// t >= tmin, equal t resolved to the lower primitive id — but cut into single steps (node_step / leaf_step)
+// whose state lives in Trav and the per-lane stack, so a warp can decide by ballot WHICH step its lanes take
+// next (persist.cu).  A lane that reaches a leaf may wait a few node steps of its neighbours before the leaf
+// is tested, i.e. pruning may use a slightly stale `best`; that only costs a few extra node visits, the
+// closest hit is order-independent.
+#define PT_SENTINEL PT_NO_BVH
+#define PT_STACK 64
+
+struct Trav {
+    float3 inv, oi;  // slab operands: t = box * inv + oi
+    float best;      // closest accepted t so far (tmax before any hit)
+    Hit h;
+    int cur;         // >= 0 inner node, < 0 leaf ~prim, PT_SENTINEL = finished
+    int sp;
+};
+
+template <bool COUNT>
+PT_DEV void trav_begin(const SceneView& sv, float3 o, float3 d, float tmin, float tmax, Trav& T, int* stack,
+                       TraceCounters& tc) {
+    T.h.t = -1.0f; T.h.prim = -1; T.h.u = 0.0f; T.h.v = 0.0f;
+    T.best = tmax;
+#pragma unroll
+    for (int g = 0; g < PT_MAX_INLINE; ++g) {
+        if (g < sv.n_inl) {
+            if (COUNT) tc.prims++;
+            float t;
+            const int p = sv.inl_id[g];
+            if (sphere_hit_ref(o, d, sv.inl_cr[g], sv.inl_r2[g], sv.inl_transparent[g] != 0, &t) && t >= tmin &&
+                (t < T.best || (t == T.best && p < T.h.prim))) {
+                T.best = t;
+                T.h.t = t; T.h.prim = p;
+            }
+        }
+    }
+    for (int g = 0; g < sv.n_global; ++g) test_prim<COUNT>(sv, __ldg(&sv.global_prims[g]), o, d, tmin, T.h, T.best, tc);
+    T.inv = f3(1.0f / (fabsf(d.x) < 1e-18f ? copysignf(1e-18f, d.x) : d.x),
+               1.0f / (fabsf(d.y) < 1e-18f ? copysignf(1e-18f, d.y) : d.y),
+               1.0f / (fabsf(d.z) < 1e-18f ? copysignf(1e-18f, d.z) : d.z));
+    T.oi = f3(-o.x * T.inv.x, -o.y * T.inv.y, -o.z * T.inv.z);
+    stack[0] = PT_SENTINEL;
+    T.sp = 1;
+    T.cur = sv.root;
+    if (T.cur < 0) {  // degenerate tree: the root is a leaf
+        test_prim<COUNT>(sv, ~T.cur, o, d, tmin, T.h, T.best, tc);
+        T.cur = PT_SENTINEL;
+    }
+}
+
+// 64-byte BVH2 node as two 256-bit loads (LDG.E.ENL2.256, new with sm_100): the L1 spends one tag
+// lookup per lane and instruction on these divergent fetches, so two wide loads cost half of four LDG.128
+// (profiles/r01_trace_persist_v2_summary.txt: l1tex throughput 96 % with four).
+struct __align__(32) Node8 {
+    float v[8];
+};
+PT_DEV Node8 ldg256(const void* p) {
+    Node8 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+        : "l"(p));
+    return r;
+}
+
+#define PT_IS_INNER(c) ((unsigned)(c) < (unsigned)PT_SENTINEL)
+
+// One inner-node step of the ordered traversal: tests both child boxes of node T.cur, descends into the
+// nearer hit child (pushing the farther one) or pops.  Afterwards T.cur is an inner node, a leaf (< 0) or
+// PT_SENTINEL.
+template <bool COUNT>
+PT_DEV void node_step(const SceneView& sv, Trav& T, int* stack, TraceCounters& tc) {
+    if (COUNT) tc.nodes++;
+    const float4* n = sv.nodes + 4 * (size_t)T.cur;
+    const Node8 A = ldg256(n), B = ldg256(n + 2);
+    // child 0: min A0 A1 A2 max A3 A4 A5; child 1: min A6 A7 B0 max B1 B2 B3; refs B4 B5
+    const float3 inv = T.inv, oi = T.oi;
+    float x0 = fmaf(A.v[0], inv.x, oi.x), x1 = fmaf(A.v[3], inv.x, oi.x);
+    float y0 = fmaf(A.v[1], inv.y, oi.y), y1 = fmaf(A.v[4], inv.y, oi.y);
+    float z0 = fmaf(A.v[2], inv.z, oi.z), z1 = fmaf(A.v[5], inv.z, oi.z);
+    const float t0a = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+    const float t1a = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), T.best));
+    x0 = fmaf(A.v[6], inv.x, oi.x); x1 = fmaf(B.v[1], inv.x, oi.x);
+    y0 = fmaf(A.v[7], inv.y, oi.y); y1 = fmaf(B.v[2], inv.y, oi.y);
+    z0 = fmaf(B.v[0], inv.z, oi.z); z1 = fmaf(B.v[3], inv.z, oi.z);
+    const float t0b = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+    const float t1b = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), T.best));
+    const bool ha = t0a <= t1a, hb = t0b <= t1b;
+    const int ca = __float_as_int(B.v[4]), cb = __float_as_int(B.v[5]);
+    if (ha && hb) {
+        const bool a_first = t0a <= t0b;
+        stack[T.sp++] = a_first ? cb : ca;
+        T.cur = a_first ? ca : cb;
+    } else if (ha || hb) {
+        T.cur = ha ? ca : cb;
+    } else {
+        T.cur = stack[--T.sp];
+    }
+}
+
+// Leaf step: tests primitive ~T.cur and pops.
+template <bool COUNT>
+PT_DEV void leaf_step(const SceneView& sv, float3 o, float3 d, float tmin, Trav& T, int* stack, TraceCounters& tc) {
+    test_prim<COUNT>(sv, ~T.cur, o, d, tmin, T.h, T.best, tc);
+    T.cur = stack[--T.sp];
+}

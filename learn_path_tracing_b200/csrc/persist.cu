@@ -1,0 +1,354 @@
+// persist.cu — persistent, ballot-scheduled kernels for scenes that have a BVH (PT_MODE_PERSIST).
+//
+// ncu on the K-step fused wavefront (k_paths) and on the one-ray-per-thread k_trace showed 6.0 / 6.7
+// active threads per warp instruction on the mesh scenes and the 10M-triangle batch
+// (profiles/r01_paths_yoimiya_v1_summary.txt, r01_trace_v1_summary.txt): a lane that misses everything
+// waits for its neighbour's 100-node traversal, and lanes in a leaf wait for lanes in inner nodes.
+// Here every LANE is its own small state machine (inner node / leaf / finished / idle) and the WARP votes
+// by ballot on what to run next:
+//
+//   node phase     all lanes standing on an inner node take one node_step (two 256-bit loads, two slab
+//                  tests); repeated while few lanes are waiting for anything else
+//   service        entered once `serve_min` more lanes wait (at a leaf, finished, idle) than after the
+//                  previous service, or nobody walks any more:
+//     leaf phase     lanes on a leaf test their primitive and pop
+//     shade phase    (render kernel, once >= shade_min lanes finished) miss -> RED.v4 into the
+//                    accumulator, hit -> scatter; idle lanes take the next path of the warp's work unit
+//                    and generate their camera ray in place (fused ray generation)
+//     refill         (trace kernel) finished lanes write their hit record and draw the next ray
+//
+// A work unit of the render kernel is one 8x4 pixel tile x 16 samples, taken from ONE global counter
+// (one atomic per 512 paths); the lanes of a warp therefore always look at the same 32 pixels, which
+// keeps their rays — and their behaviour (all sky, all ground, all mesh) — alike.  One launch renders
+// everything: no path pool in HBM, no per-bounce launches; HBM only sees the scene and the accumulator.
+// The RNG is keyed on (pixel, sample, bounce), so the image is the same set of paths as the other modes.
+#include <cub/device/device_radix_sort.cuh>
+#include <math.h>
+#include <string.h>
+
+#include "wf_common.cuh"
+
+#define ST_IDLE 0  // needs a new path
+#define ST_TRAV 1  // traversal in progress (T.cur: inner node, leaf or PT_SENTINEL = finished)
+#define ST_DEAD 2  // no work left for this lane
+
+#define PT_TILE_W 8
+#define PT_TILE_H 4
+#define PT_UNIT_SAMPLES 16
+
+template <bool LEGACY, bool COUNT>
+__global__ void __launch_bounds__(PT_BLOCK, 4)
+k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* __restrict__ counters,
+                float4* __restrict__ accum, float4* __restrict__ accum_sq, int shade_min, int serve_min) {
+    int stack[PT_STACK];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned tiles_x = ((unsigned)rc.W + PT_TILE_W - 1) / PT_TILE_W, tiles_y = ((unsigned)rc.H + PT_TILE_H - 1) / PT_TILE_H;
+    const unsigned spp = rc.sample_end - rc.spp_offset;
+    const unsigned n_chunks = (spp + PT_UNIT_SAMPLES - 1) / PT_UNIT_SAMPLES;
+    const unsigned long long n_units = (unsigned long long)tiles_x * tiles_y * n_chunks;
+    PathState p;
+    Trav T;
+    T.cur = PT_SENTINEL; T.sp = 1;
+    int st = ST_IDLE;
+    // warp-uniform: the work unit in progress and the next path of it
+    unsigned unit_x0 = 0, unit_y0 = 0, unit_s0 = 0, unit_ns = 0, unit_next = 0, unit_size = 0;
+    bool exhausted = false;  // the global unit counter has run past n_units
+    unsigned wait_base = 0;  // lanes that were still waiting after the last service
+    unsigned nseg = 0;
+    TraceCounters tc;
+    tc.nodes = 0; tc.prims = 0;
+
+    for (;;) {
+        const bool inner = st == ST_TRAV && PT_IS_INNER(T.cur);
+        const unsigned m_inner = __ballot_sync(0xffffffffu, inner);
+        if (m_inner != 0u && (unsigned)__popc(~m_inner) < wait_base + (unsigned)serve_min) {
+            if (inner) node_step<COUNT>(sv, T, stack, tc);
+            continue;
+        }
+        // ---- service ---------------------------------------------------------------------------------
+        if (st == ST_TRAV && T.cur < 0) leaf_step<COUNT>(sv, p.o, p.d, rc.tmin, T, stack, tc);
+        __syncwarp();
+        const unsigned m_fin = __ballot_sync(0xffffffffu, st == ST_TRAV && T.cur == PT_SENTINEL);
+        const unsigned m_idle = __ballot_sync(0xffffffffu, st == ST_IDLE);
+        const unsigned m_walk = __ballot_sync(0xffffffffu, st == ST_TRAV && T.cur != PT_SENTINEL);
+        if ((m_fin | m_idle) != 0u && (m_walk == 0u || (unsigned)__popc(m_fin | m_idle) >= (unsigned)shade_min)) {
+            if (st == ST_TRAV && T.cur == PT_SENTINEL) {  // ---- shade
+                bool alive = false;
+                if (T.h.prim < 0) {  // miss: sky / environment radiance * throughput, path ends
+                    const float3 c = (LEGACY ? environment_color(sv, p.d) : sky_color(p.d)) * p.l;
+                    if (isfinite(c.x) && isfinite(c.y) && isfinite(c.z)) {
+                        atomicAdd(&accum[p.pixel], make_float4(c.x, c.y, c.z, 1.0f));
+                        if (rc.accum_sq) atomicAdd(&accum_sq[p.pixel], make_float4(c.x * c.x, c.y * c.y, c.z * c.z, 1.0f));
+                    }
+                } else {
+                    T.h.t = T.best;
+                    if (LEGACY) scatter_legacy(sv, p, T.h, rc.absorptivity, rc.seed);
+                    else scatter_v2(sv, p, T.h, rc.shading_model, rc.seed);
+                    p.bounce += 1u;
+                    alive = p.bounce < (uint32_t)rc.max_depth;  // over propagate_limit: contributes nothing
+                }
+                st = alive ? ST_TRAV : ST_IDLE;
+                if (alive) {
+                    trav_begin<COUNT>(sv, p.o, p.d, rc.tmin, INFINITY, T, stack, tc);
+                    ++nseg;
+                }
+            }
+            __syncwarp();
+            // ---- refill idle lanes from the warp's work unit; take the next unit when it runs out
+            for (;;) {
+                const unsigned idle = __ballot_sync(0xffffffffu, st == ST_IDLE);
+                if (idle == 0u) break;
+                if (unit_next >= unit_size) {
+                    if (exhausted) {
+                        if (st == ST_IDLE) st = ST_DEAD;
+                        break;
+                    }
+                    unsigned long long u = 0ull;
+                    if (lane == 0u) u = atomicAdd(&counters[CNT_NEXT_PATH], 1ull);
+                    u = __shfl_sync(0xffffffffu, u, 0);
+                    if (u >= n_units) {
+                        exhausted = true;
+                        continue;
+                    }
+                    const unsigned tile = (unsigned)(u / n_chunks), chunk = (unsigned)(u - (unsigned long long)tile * n_chunks);
+                    const unsigned ty = tile / tiles_x;
+                    unit_x0 = (tile - ty * tiles_x) * PT_TILE_W;
+                    unit_y0 = ty * PT_TILE_H;
+                    unit_s0 = chunk * PT_UNIT_SAMPLES;
+                    unit_ns = min((unsigned)PT_UNIT_SAMPLES, spp - unit_s0);
+                    unit_size = unit_ns * 32u;
+                    unit_next = 0u;
+                }
+                const unsigned take = min((unsigned)__popc(idle), unit_size - unit_next);
+                if (st == ST_IDLE) {
+                    const unsigned r = __popc(idle & lt);
+                    if (r < take) {
+                        const unsigned q = unit_next + r;
+                        const unsigned px = unit_x0 + (q & 7u), py = unit_y0 + ((q >> 3) & 3u);
+                        if (px < (unsigned)rc.W && py < (unsigned)rc.H) {  // image sizes need not be tile multiples
+                            p.pixel = py * (unsigned)rc.W + px;
+                            p.sample = rc.spp_offset + unit_s0 + (q >> 5);
+                            p.bounce = 0u;
+                            p.l = f3(1.0f, 1.0f, 1.0f);
+                            camera_ray(rc.cam, (int)px, (int)py, rng4(p.pixel, p.sample, 0u, rc.seed), &p.o, &p.d);
+                            trav_begin<COUNT>(sv, p.o, p.d, rc.tmin, INFINITY, T, stack, tc);
+                            ++nseg;
+                            st = ST_TRAV;
+                        }
+                    }
+                }
+                unit_next += take;
+            }
+            __syncwarp();
+        }
+        const unsigned m_wait = __ballot_sync(0xffffffffu, !(st == ST_TRAV && PT_IS_INNER(T.cur)));
+        if (m_wait == 0xffffffffu && __ballot_sync(0xffffffffu, st != ST_DEAD) == 0u) break;  // every lane is dead
+        // lanes that still wait (finished but not yet shaded, dead) do not count towards the next trigger
+        wait_base = __popc(__ballot_sync(0xffffffffu, st != ST_TRAV || T.cur == PT_SENTINEL));
+    }
+    nseg += __shfl_xor_sync(0xffffffffu, nseg, 16);
+    nseg += __shfl_xor_sync(0xffffffffu, nseg, 8);
+    nseg += __shfl_xor_sync(0xffffffffu, nseg, 4);
+    nseg += __shfl_xor_sync(0xffffffffu, nseg, 2);
+    nseg += __shfl_xor_sync(0xffffffffu, nseg, 1);
+    if (lane == 0 && nseg) atomicAdd(&counters[CNT_SEGMENTS], (unsigned long long)nseg);
+    if (COUNT) {
+        atomicAdd(&counters[CNT_NODES], (unsigned long long)tc.nodes);
+        atomicAdd(&counters[CNT_PRIMS], (unsigned long long)tc.prims);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fixed ray batch (pt_trace_batch*, BASELINE configs[4]): persistent warps, rays drawn dynamically from
+// one counter in the order given by `order` (a sort by entry point and direction, see k_ray_keys; NULL =
+// batch order).  Result i is written to hits[i] of the ORIGINAL batch order.
+template <bool COUNT>
+__global__ void __launch_bounds__(PT_BLOCK, 4)
+k_trace_persist(const SceneView sv, const float4* __restrict__ rays, const unsigned* __restrict__ order,
+                float4* __restrict__ hits, long long n, unsigned long long* __restrict__ counters, int serve_min,
+                int fetch_min) {
+    int stack[PT_STACK];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt = (1u << lane) - 1u;
+    float3 o = f3(0, 0, 0), d = f3(0, 0, 1);
+    float tmin = 0.0f;
+    long long ray = -1;
+    Trav T;
+    T.cur = PT_SENTINEL; T.sp = 1;
+    int st = ST_IDLE;
+    bool exhausted = false;
+    unsigned wait_base = 0;
+    TraceCounters tc;
+    tc.nodes = 0; tc.prims = 0;
+    for (;;) {
+        const bool inner = st == ST_TRAV && PT_IS_INNER(T.cur);
+        const unsigned m_inner = __ballot_sync(0xffffffffu, inner);
+        if (m_inner != 0u && (unsigned)__popc(~m_inner) < wait_base + (unsigned)serve_min) {
+            if (inner) node_step<COUNT>(sv, T, stack, tc);
+            continue;
+        }
+        // ---- service: leaves, then results + refill ------------------------------------------------------
+        if (st == ST_TRAV && T.cur < 0) leaf_step<COUNT>(sv, o, d, tmin, T, stack, tc);
+        __syncwarp();
+        const unsigned m_fin = __ballot_sync(0xffffffffu, st == ST_TRAV && T.cur == PT_SENTINEL);
+        const unsigned m_idle = __ballot_sync(0xffffffffu, st == ST_IDLE);
+        const unsigned m_walk = __ballot_sync(0xffffffffu, st == ST_TRAV && T.cur != PT_SENTINEL);
+        if ((m_fin | m_idle) != 0u && (m_walk == 0u || (unsigned)__popc(m_fin | m_idle) >= (unsigned)fetch_min)) {
+            if (st == ST_TRAV && T.cur == PT_SENTINEL) {
+                hits[ray] = make_float4(T.h.prim >= 0 ? T.best : -1.0f, __int_as_float(T.h.prim), T.h.u, T.h.v);
+                st = ST_IDLE;
+            }
+            const unsigned idle = m_fin | m_idle;
+            if (!exhausted) {
+                const unsigned cnt = __popc(idle);
+                unsigned long long base = 0ull;
+                if (lane == 0u) base = atomicAdd(&counters[CNT_NEXT_PATH], (unsigned long long)cnt);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                exhausted = (long long)(base + cnt) >= n;
+                if (st == ST_IDLE) {
+                    const long long k = (long long)base + __popc(idle & lt);
+                    if (k < n) {
+                        ray = order ? (long long)__ldg(&order[k]) : k;
+                        const float4 ro = __ldg(&rays[2 * ray]), rd = __ldg(&rays[2 * ray + 1]);
+                        o = f3(ro); d = f3(rd); tmin = ro.w;
+                        trav_begin<COUNT>(sv, o, d, tmin, rd.w, T, stack, tc);
+                        st = ST_TRAV;
+                    } else {
+                        st = ST_DEAD;
+                    }
+                }
+            } else if (st == ST_IDLE) {
+                st = ST_DEAD;
+            }
+            __syncwarp();
+        }
+        if (__ballot_sync(0xffffffffu, st != ST_DEAD) == 0u) break;
+        wait_base = __popc(__ballot_sync(0xffffffffu, st != ST_TRAV || T.cur == PT_SENTINEL));
+    }
+    if (COUNT) {
+        atomicAdd(&counters[CNT_NODES], (unsigned long long)tc.nodes);
+        atomicAdd(&counters[CNT_PRIMS], (unsigned long long)tc.prims);
+    }
+}
+
+// Sort key of a ray: Morton code over (entry point into the scene box: 3 x 6 bits, direction in the
+// octahedral map: 2 x 6 bits), bits interleaved so that a run of consecutive keys is a thin beam.
+PT_DEV unsigned spread5(unsigned v) {  // 6 bits -> every fifth bit
+    unsigned r = 0;
+#pragma unroll
+    for (int b = 0; b < 6; ++b) r |= ((v >> b) & 1u) << (5 * b);
+    return r;
+}
+__global__ void k_ray_keys(const float4* __restrict__ rays, long long n, float3 lo, float3 inv_ext,
+                           unsigned* __restrict__ keys, unsigned* __restrict__ vals) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float4 ro = __ldg(&rays[2 * k]), rd = __ldg(&rays[2 * k + 1]);
+    const float3 o = f3(ro), d = f3(rd);
+    // entry point into the scene box (the origin when it is inside or the ray misses the box)
+    const float3 inv = f3(1.0f / (fabsf(d.x) < 1e-18f ? copysignf(1e-18f, d.x) : d.x),
+                          1.0f / (fabsf(d.y) < 1e-18f ? copysignf(1e-18f, d.y) : d.y),
+                          1.0f / (fabsf(d.z) < 1e-18f ? copysignf(1e-18f, d.z) : d.z));
+    const float3 hi = f3(lo.x + 1.0f / inv_ext.x, lo.y + 1.0f / inv_ext.y, lo.z + 1.0f / inv_ext.z);
+    const float ax = (lo.x - o.x) * inv.x, bx = (hi.x - o.x) * inv.x;
+    const float ay = (lo.y - o.y) * inv.y, by = (hi.y - o.y) * inv.y;
+    const float az = (lo.z - o.z) * inv.z, bz = (hi.z - o.z) * inv.z;
+    const float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+    const float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    const float te = t0 <= t1 ? t0 : 0.0f;
+    const float px = (o.x + te * d.x - lo.x) * inv_ext.x, py = (o.y + te * d.y - lo.y) * inv_ext.y,
+                pz = (o.z + te * d.z - lo.z) * inv_ext.z;
+    // octahedral map of the direction -> [0,1)^2
+    const float s = 1.0f / (fabsf(d.x) + fabsf(d.y) + fabsf(d.z));
+    float ux = d.x * s, uy = d.y * s;
+    if (d.z < 0.0f) {
+        const float tx = (1.0f - fabsf(uy)) * (ux >= 0.0f ? 1.0f : -1.0f);
+        const float ty = (1.0f - fabsf(ux)) * (uy >= 0.0f ? 1.0f : -1.0f);
+        ux = tx; uy = ty;
+    }
+    const float S = 64.0f;
+    const unsigned qx = (unsigned)fminf(fmaxf(px * S, 0.0f), S - 1.0f), qy = (unsigned)fminf(fmaxf(py * S, 0.0f), S - 1.0f),
+                   qz = (unsigned)fminf(fmaxf(pz * S, 0.0f), S - 1.0f);
+    const unsigned qu = (unsigned)fminf(fmaxf((0.5f * ux + 0.5f) * S, 0.0f), S - 1.0f),
+                   qv = (unsigned)fminf(fmaxf((0.5f * uy + 0.5f) * S, 0.0f), S - 1.0f);
+    keys[k] = spread5(qx) << 4 | spread5(qy) << 3 | spread5(qz) << 2 | spread5(qu) << 1 | spread5(qv);
+    vals[k] = (unsigned)k;
+}
+
+static int ensure_sort_scratch(PtContext* ctx, size_t bytes) {
+    if (bytes <= ctx->sort_bytes) return PT_OK;
+    if (ctx->sort_scratch) cudaFree(ctx->sort_scratch);
+    ctx->sort_scratch = nullptr;
+    ctx->sort_bytes = 0;
+    PT_CUDA(cudaMalloc(&ctx->sort_scratch, bytes));
+    ctx->sort_bytes = bytes;
+    return PT_OK;
+}
+
+// Persistent grid: as many blocks as are resident at once.
+template <class K>
+static int resident_blocks(PtContext* ctx, K kernel, int* out) {
+    int per_sm = 0;
+    PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, PT_BLOCK, 0));
+    if (per_sm < 1) per_sm = 1;
+    *out = per_sm * ctx->sm_count;
+    return PT_OK;
+}
+
+int pt_trace_persist(PtContext* ctx, const PtScene* s, const float4* rays, long long n, float4* hits, bool count,
+                     bool sort, int serve_min, int fetch_min, float* ms_sort) {
+    cudaStream_t st = ctx->stream;
+    const unsigned* order = nullptr;
+    if (ms_sort) *ms_sort = 0.0f;
+    if (sort && n > 1) {
+        PT_REQUIRE(n < (1ll << 32), "ray batches are limited to 2^32 - 1 rays");
+        size_t tmp_bytes = 0;
+        cub::DoubleBuffer<unsigned> kb(nullptr, nullptr), vb(nullptr, nullptr);
+        PT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb, vb, (int)n, 0, 30, st));
+        const size_t arr = ((size_t)n * sizeof(unsigned) + 255) / 256 * 256;
+        int rcs = ensure_sort_scratch(ctx, 4 * arr + tmp_bytes);
+        if (rcs) return rcs;
+        char* base = (char*)ctx->sort_scratch;
+        kb = cub::DoubleBuffer<unsigned>((unsigned*)base, (unsigned*)(base + arr));
+        vb = cub::DoubleBuffer<unsigned>((unsigned*)(base + 2 * arr), (unsigned*)(base + 3 * arr));
+        const float3 lo = make_float3(s->bounds_lo[0], s->bounds_lo[1], s->bounds_lo[2]);
+        const float3 ie = make_float3(1.0f / fmaxf(s->bounds_hi[0] - s->bounds_lo[0], 1e-30f),
+                                      1.0f / fmaxf(s->bounds_hi[1] - s->bounds_lo[1], 1e-30f),
+                                      1.0f / fmaxf(s->bounds_hi[2] - s->bounds_lo[2], 1e-30f));
+        k_ray_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rays, n, lo, ie, kb.Current(), vb.Current());
+        PT_CUDA(cub::DeviceRadixSort::SortPairs(base + 4 * arr, tmp_bytes, kb, vb, (int)n, 0, 30, st));
+        order = vb.Current();
+    }
+    int blocks = 0, rcb;
+    if (count) rcb = resident_blocks(ctx, k_trace_persist<true>, &blocks);
+    else rcb = resident_blocks(ctx, k_trace_persist<false>, &blocks);
+    if (rcb) return rcb;
+    const long long need = (n + PT_BLOCK - 1) / PT_BLOCK;
+    if (blocks > need) blocks = (int)need;
+    if (count) k_trace_persist<true><<<blocks, PT_BLOCK, 0, st>>>(s->view, rays, order, hits, n, ctx->counters, serve_min, fetch_min);
+    else k_trace_persist<false><<<blocks, PT_BLOCK, 0, st>>>(s->view, rays, order, hits, n, ctx->counters, serve_min, fetch_min);
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+int pt_render_persist(PtContext* ctx, const PtScene* s, const RenderConsts& rc, bool legacy, bool count, float4* accum,
+                      float4* accum_sq, int shade_min, int serve_min) {
+    cudaStream_t st = ctx->stream;
+    int blocks = 0, rcb;
+    if (legacy) rcb = count ? resident_blocks(ctx, k_paths_persist<true, true>, &blocks) : resident_blocks(ctx, k_paths_persist<true, false>, &blocks);
+    else rcb = count ? resident_blocks(ctx, k_paths_persist<false, true>, &blocks) : resident_blocks(ctx, k_paths_persist<false, false>, &blocks);
+    if (rcb) return rcb;
+    const unsigned long long need = (rc.total_paths + PT_BLOCK - 1) / PT_BLOCK;
+    if ((unsigned long long)blocks > need) blocks = (int)need;
+    if (blocks < 1) return PT_OK;
+    if (legacy) {
+        if (count) k_paths_persist<true, true><<<blocks, PT_BLOCK, 0, st>>>(s->view, rc, ctx->counters, accum, accum_sq, shade_min, serve_min);
+        else k_paths_persist<true, false><<<blocks, PT_BLOCK, 0, st>>>(s->view, rc, ctx->counters, accum, accum_sq, shade_min, serve_min);
+    } else {
+        if (count) k_paths_persist<false, true><<<blocks, PT_BLOCK, 0, st>>>(s->view, rc, ctx->counters, accum, accum_sq, shade_min, serve_min);
+        else k_paths_persist<false, false><<<blocks, PT_BLOCK, 0, st>>>(s->view, rc, ctx->counters, accum, accum_sq, shade_min, serve_min);
+    }
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}

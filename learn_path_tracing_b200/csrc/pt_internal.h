@@ -75,6 +75,9 @@ struct PtContext {
     // grow-only device scratch for host-layout read-backs (no cudaMalloc/cudaFree on the render path)
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // grow-only device scratch of the ray sort (keys, order, cub temporaries)
+    void* sort_scratch = nullptr;
+    size_t sort_bytes = 0;
 };
 
 struct HostMesh {
@@ -105,6 +108,7 @@ struct PtScene {
     std::vector<int32_t> h_global;
     int64_t n_nodes = 0;
     bool built = false;
+    float bounds_lo[3] = {0, 0, 0}, bounds_hi[3] = {1, 1, 1};  // box of the LBVH root (ray-sort quantisation)
     SceneView view{};
 };
 
@@ -134,5 +138,11 @@ int pt_lbvh_build(PtContext* ctx, const float4* d_prim_aabb, const int* d_local_
 
 // wavefront.cu
 int pt_ensure_pool(PtContext* ctx, size_t capacity);
+// persist.cu — persistent while-while kernels (PT_MODE_PERSIST)
+struct RenderConsts;
+int pt_render_persist(PtContext* ctx, const PtScene* s, const RenderConsts& rc, bool legacy, bool count, float4* accum,
+                      float4* accum_sq, int shade_min, int serve_min);
+int pt_trace_persist(PtContext* ctx, const PtScene* s, const float4* rays, long long n, float4* hits, bool count,
+                     bool sort, int serve_min, int fetch_min, float* ms_sort);
 // post.cu
 int pt_ensure_scratch(PtContext* ctx, size_t bytes);

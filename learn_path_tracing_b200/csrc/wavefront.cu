@@ -22,42 +22,7 @@
 #include <math.h>
 #include <string.h>
 
-#include "shade.cuh"
-
-#define PT_BLOCK 256
-#define PT_WARPS (PT_BLOCK / 32)
-
-// device counter block (unsigned long long[16])
-#define CNT_NEXT_PATH 0
-#define CNT_SEGMENTS 1
-#define CNT_NODES 2
-#define CNT_PRIMS 3
-#define CNT_QUEUE 8  // [8], [9]: ping-pong queue sizes (low 32 bits used)
-#define CNT_WORDS 16
-#define CNT_LIVE 16  // fused mode: live-path count after launch L at [CNT_LIVE + L]
-#define PT_MAX_LAUNCHES 4080
-#define CNT_TOTAL_WORDS (CNT_LIVE + PT_MAX_LAUNCHES)
-#define PT_MODE_AUTO 0
-#define PT_MODE_SPLIT 1
-#define PT_MODE_FUSED 2
-
-struct RenderConsts {
-    CameraDev cam;
-    unsigned long long total_paths;
-    int W, H;
-    uint32_t seed, spp_offset;
-    int max_depth, shading_model;
-    float absorptivity, tmin;
-    unsigned pool_cap;
-    int accum_sq;
-    // fused mode: static striding of path ids over the pool, id -> (sample, pixel) without division
-    uint32_t stride_samples, stride_pixels;  // pool_cap = stride_samples * W*H + stride_pixels
-    uint32_t sample_end;                     // spp_offset + spp
-};
-
-struct PoolPtrs {
-    float4 *o, *d, *l;
-};
+#include "wf_common.cuh"
 
 // ------------------------------------------------------------------------------------------------
 template <bool COUNT>
@@ -189,16 +154,6 @@ k_shade(const SceneView sv, const RenderConsts rc, const PoolPtrs in, const floa
 
 // ------------------------------------------------------------------------------------------------
 // Fused wavefront step: up to K ray segments per path slot per launch, state in registers.
-PT_DEV void start_path(const RenderConsts& rc, PathState& p, uint32_t pixel, uint32_t sample) {
-    p.pixel = pixel;
-    p.sample = sample;
-    p.bounce = 0u;
-    p.l = f3(1.0f, 1.0f, 1.0f);
-    const float4 u = rng4(pixel, sample, 0u, rc.seed);
-    const uint32_t j = pixel / (uint32_t)rc.W;
-    camera_ray(rc.cam, (int)(pixel - j * (uint32_t)rc.W), (int)j, u, &p.o, &p.d);
-}
-
 template <bool LEGACY, bool COUNT>
 __global__ void __launch_bounds__(PT_BLOCK, 4)
 k_paths(const SceneView sv, const RenderConsts rc, const PoolPtrs in, const PoolPtrs out,
@@ -489,9 +444,13 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
     PT_REQUIRE(!legacy || s->view.n_sph == 0 || s->view.legacy_spheres, "legacy shading needs legacy (textured) spheres");
     const bool want_sq = (p->flags & PT_FLAG_ACCUM_SQ) != 0;
     PT_REQUIRE(!want_sq || accum_sq_dev, "PT_FLAG_ACCUM_SQ needs accum_sq");
-    const int mode = p->reserved[0] == PT_MODE_SPLIT ? PT_MODE_SPLIT : PT_MODE_FUSED;
-    PT_REQUIRE(p->reserved[0] >= 0 && p->reserved[0] <= 2, "reserved[0] (wavefront mode) must be 0, 1 or 2");
+    PT_REQUIRE(p->reserved[0] >= 0 && p->reserved[0] <= 3, "reserved[0] (wavefront mode) must be 0, 1, 2 or 3");
     PT_REQUIRE(p->reserved[1] >= 0 && p->reserved[1] <= 4096, "reserved[1] (segments per launch) out of range");
+    PT_REQUIRE(p->reserved[2] >= 0 && p->reserved[2] <= 32 && p->reserved[3] >= 0 && p->reserved[3] <= 32,
+               "reserved[2]/[3] (persistent-mode lane thresholds) must be in [0,32]");
+    // auto: scenes with a BVH take the persistent while-while kernel, tree-less scenes the K-step fused wavefront
+    const int mode = p->reserved[0] != PT_MODE_AUTO ? p->reserved[0]
+                     : (s->view.root != PT_NO_BVH ? PT_MODE_PERSIST : PT_MODE_FUSED);
     PT_CUDA(cudaSetDevice(ctx->device));
 
     const unsigned long long total = (unsigned long long)p->width * p->height * (unsigned long long)p->spp;
@@ -499,7 +458,7 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
     size_t cap = p->pool_capacity > 0 ? (size_t)p->pool_capacity : def_cap;
     if (cap > total) cap = (size_t)total;
     cap = (cap + PT_BLOCK - 1) / PT_BLOCK * PT_BLOCK;
-    if (cap < PT_BLOCK) cap = PT_BLOCK;
+    if (cap < PT_BLOCK || mode == PT_MODE_PERSIST) cap = PT_BLOCK;  // the persistent kernel keeps no pool in HBM
     int rc_pool = pt_ensure_pool(ctx, cap);
     if (rc_pool) return rc_pool;
 
@@ -526,7 +485,16 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
 
     int iterations = 0, launches = 0, rcode;
     size_t ev_idx = 0;
-    if (mode == PT_MODE_SPLIT)
+    if (mode == PT_MODE_PERSIST) {
+        // warp votes (persist.cu): a service (leaf tests, shading, refill) starts once serve_min more lanes wait
+        // than after the previous one; finished lanes are shaded once shade_min of them have piled up
+        const int shade_min = p->reserved[2] > 0 ? p->reserved[2] : 12;
+        const int serve_min = p->reserved[3] > 0 ? p->reserved[3] : 8;
+        if (timing) cudaEventRecord(get_event(ctx, ev_idx++), st);
+        rcode = pt_render_persist(ctx, s, rc, legacy, count, (float4*)accum_dev, (float4*)accum_sq_dev, shade_min, serve_min);
+        if (timing) cudaEventRecord(get_event(ctx, ev_idx++), st);
+        iterations = 1; launches = 1;
+    } else if (mode == PT_MODE_SPLIT)
         rcode = render_split(ctx, s, rc, legacy, timing, count, (float4*)accum_dev, (float4*)accum_sq_dev, &iterations, &launches, &ev_idx);
     else
         rcode = render_fused(ctx, s, rc, legacy, timing, count, (float4*)accum_dev, (float4*)accum_sq_dev,
@@ -594,9 +562,17 @@ extern "C" int pt_trace_batch_device(PtContext* ctx, const PtScene* s, const voi
     PT_CUDA(cudaMemsetAsync(ctx->counters, 0, CNT_WORDS * sizeof(unsigned long long), st));
     PT_CUDA(cudaEventRecord(ctx->ev_a, st));
     if (n > 0) {
-        const unsigned blocks = (unsigned)((n + PT_BLOCK - 1) / PT_BLOCK);
-        if (count) k_trace<true><<<blocks, PT_BLOCK, 0, st>>>(s->view, (const float4*)rays_dev, (float4*)hits_dev, n, ctx->counters);
-        else k_trace<false><<<blocks, PT_BLOCK, 0, st>>>(s->view, (const float4*)rays_dev, (float4*)hits_dev, n, ctx->counters);
+        if ((flags & PT_FLAG_TRACE_SIMPLE) || s->view.root == PT_NO_BVH) {  // one ray per thread, batch order
+            const unsigned blocks = (unsigned)((n + PT_BLOCK - 1) / PT_BLOCK);
+            if (count) k_trace<true><<<blocks, PT_BLOCK, 0, st>>>(s->view, (const float4*)rays_dev, (float4*)hits_dev, n, ctx->counters);
+            else k_trace<false><<<blocks, PT_BLOCK, 0, st>>>(s->view, (const float4*)rays_dev, (float4*)hits_dev, n, ctx->counters);
+        } else {  // persistent while-while warps over the (sorted) batch
+            const bool sort = !(flags & PT_FLAG_NO_SORT) && n >= (1 << 16);
+            const int serve_min = (flags >> 8) & 63, fetch_min = (flags >> 14) & 63;
+            int rct = pt_trace_persist(ctx, s, (const float4*)rays_dev, n, (float4*)hits_dev, count, sort,
+                                       serve_min ? serve_min : 8, fetch_min ? fetch_min : 8, nullptr);
+            if (rct) return rct;
+        }
     }
     PT_CUDA(cudaEventRecord(ctx->ev_b, st));
     PT_CUDA(cudaGetLastError());

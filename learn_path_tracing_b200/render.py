@@ -51,7 +51,7 @@ class Renderer:
     def render(self, scene: _lib.Scene, cam: _lib.PtCamera, spp: int, max_depth: int,
                shading_model: int = _lib.PT_SHADE_V2, seed: int = 1, spp_offset: int | None = None,
                absorptivity: float = 0.25, flags: int = 0, pool_capacity: int = 0, mode: int = 0,
-               segments_per_launch: int = 0) -> _lib.PtStats:
+               segments_per_launch: int = 0, shade_min: int = 0, serve_min: int = 0) -> _lib.PtStats:
         """Adds `spp` more samples per pixel into the accumulators (progressive, legacy render(moved=False))."""
         p = _lib.PtRenderParams()
         p.width, p.height = self.width, self.height
@@ -63,7 +63,9 @@ class Renderer:
         p.absorptivity = float(absorptivity)
         p.pool_capacity = int(pool_capacity)
         p.flags = int(flags) | (_lib.PT_FLAG_ACCUM_SQ if self.accum_sq is not None else 0)
-        p.reserved[0] = int(mode)                 # 0 auto (fused), 1 split extend/shade kernels, 2 fused k_paths
+        p.reserved[0] = int(mode)                 # 0 auto, 1 split extend/shade kernels, 2 fused k_paths, 3 persistent
+        p.reserved[2] = int(shade_min)            # persistent: finished lanes that trigger shading/refill (0 = default)
+        p.reserved[3] = int(serve_min)            # persistent: waiting lanes that trigger a service (0 = default)
         p.reserved[1] = int(segments_per_launch)  # fused: ray segments per path slot per launch (0 = 32)
         self.ctx.set_stream(self.torch.cuda.current_stream().cuda_stream)
         st = self.ctx.render(scene, cam, p, self.accum.data_ptr(),
