@@ -165,17 +165,14 @@ PT_DEV void trav_begin(const SceneView& sv, float3 o, float3 d, float tmin, floa
                        TraceCounters& tc) {
     T.h.t = -1.0f; T.h.prim = -1; T.h.u = 0.0f; T.h.v = 0.0f;
     T.best = tmax;
-#pragma unroll
-    for (int g = 0; g < PT_MAX_INLINE; ++g) {
-        if (g < sv.n_inl) {
-            if (COUNT) tc.prims++;
-            float t;
-            const int p = sv.inl_id[g];
-            if (sphere_hit_ref(o, d, sv.inl_cr[g], sv.inl_r2[g], sv.inl_transparent[g] != 0, &t) && t >= tmin &&
-                (t < T.best || (t == T.best && p < T.h.prim))) {
-                T.best = t;
-                T.h.t = t; T.h.prim = p;
-            }
+    for (int g = 0; g < sv.n_inl; ++g) {  // constant-bank operands, indexed
+        if (COUNT) tc.prims++;
+        float t;
+        const int p = sv.inl_id[g];
+        if (sphere_hit_ref(o, d, sv.inl_cr[g], sv.inl_r2[g], sv.inl_transparent[g] != 0, &t) && t >= tmin &&
+            (t < T.best || (t == T.best && p < T.h.prim))) {
+            T.best = t;
+            T.h.t = t; T.h.prim = p;
         }
     }
     for (int g = 0; g < sv.n_global; ++g) test_prim<COUNT>(sv, __ldg(&sv.global_prims[g]), o, d, tmin, T.h, T.best, tc);

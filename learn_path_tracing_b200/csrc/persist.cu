@@ -31,6 +31,7 @@
 #define ST_IDLE 0  // needs a new path
 #define ST_TRAV 1  // traversal in progress (T.cur: inner node, leaf or PT_SENTINEL = finished)
 #define ST_DEAD 2  // no work left for this lane
+#define ST_NEW 3   // has a ray (camera or scattered), traversal not started yet
 
 #define PT_TILE_W 8
 #define PT_TILE_H 4
@@ -74,24 +75,19 @@ k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* _
         const unsigned m_walk = __ballot_sync(0xffffffffu, st == ST_TRAV && T.cur != PT_SENTINEL);
         if ((m_fin | m_idle) != 0u && (m_walk == 0u || (unsigned)__popc(m_fin | m_idle) >= (unsigned)shade_min)) {
             if (st == ST_TRAV && T.cur == PT_SENTINEL) {  // ---- shade
-                bool alive = false;
                 if (T.h.prim < 0) {  // miss: sky / environment radiance * throughput, path ends
                     const float3 c = (LEGACY ? environment_color(sv, p.d) : sky_color(p.d)) * p.l;
                     if (isfinite(c.x) && isfinite(c.y) && isfinite(c.z)) {
                         atomicAdd(&accum[p.pixel], make_float4(c.x, c.y, c.z, 1.0f));
                         if (rc.accum_sq) atomicAdd(&accum_sq[p.pixel], make_float4(c.x * c.x, c.y * c.y, c.z * c.z, 1.0f));
                     }
+                    st = ST_IDLE;
                 } else {
                     T.h.t = T.best;
                     if (LEGACY) scatter_legacy(sv, p, T.h, rc.absorptivity, rc.seed);
                     else scatter_v2(sv, p, T.h, rc.shading_model, rc.seed);
                     p.bounce += 1u;
-                    alive = p.bounce < (uint32_t)rc.max_depth;  // over propagate_limit: contributes nothing
-                }
-                st = alive ? ST_TRAV : ST_IDLE;
-                if (alive) {
-                    trav_begin<COUNT>(sv, p.o, p.d, rc.tmin, INFINITY, T, stack, tc);
-                    ++nseg;
+                    st = p.bounce < (uint32_t)rc.max_depth ? ST_NEW : ST_IDLE;  // over propagate_limit: contributes nothing
                 }
             }
             __syncwarp();
@@ -132,13 +128,17 @@ k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* _
                             p.bounce = 0u;
                             p.l = f3(1.0f, 1.0f, 1.0f);
                             camera_ray(rc.cam, (int)px, (int)py, rng4(p.pixel, p.sample, 0u, rc.seed), &p.o, &p.d);
-                            trav_begin<COUNT>(sv, p.o, p.d, rc.tmin, INFINITY, T, stack, tc);
-                            ++nseg;
-                            st = ST_TRAV;
+                            st = ST_NEW;
                         }
                     }
                 }
                 unit_next += take;
+            }
+            __syncwarp();
+            if (st == ST_NEW) {  // continued and new paths start their next segment together
+                trav_begin<COUNT>(sv, p.o, p.d, rc.tmin, INFINITY, T, stack, tc);
+                ++nseg;
+                st = ST_TRAV;
             }
             __syncwarp();
         }

@@ -108,6 +108,7 @@ PT_DEV float3 sky_color(float3 d) {  // backbround_color, __main__.py:58-62
 
 // ---- legacy textures ------------------------------------------------------------------------
 PT_DEV int pymod(int a, int m) {  // ti.mod: Python modulo
+    if (m > 0 && a >= -m && a < 2 * m) return a < 0 ? a + m : (a >= m ? a - m : a);  // the usual case: no division
     int r = a % m;
     return (r != 0 && ((r < 0) != (m < 0))) ? r + m : r;
 }

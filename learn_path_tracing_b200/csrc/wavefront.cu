@@ -488,7 +488,7 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
     if (mode == PT_MODE_PERSIST) {
         // warp votes (persist.cu): a service (leaf tests, shading, refill) starts once serve_min more lanes wait
         // than after the previous one; finished lanes are shaded once shade_min of them have piled up
-        const int shade_min = p->reserved[2] > 0 ? p->reserved[2] : 12;
+        const int shade_min = p->reserved[2] > 0 ? p->reserved[2] : 22;
         const int serve_min = p->reserved[3] > 0 ? p->reserved[3] : 8;
         if (timing) cudaEventRecord(get_event(ctx, ev_idx++), st);
         rcode = pt_render_persist(ctx, s, rc, legacy, count, (float4*)accum_dev, (float4*)accum_sq_dev, shade_min, serve_min);
