@@ -55,20 +55,24 @@ k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* _
     // warp-uniform: the work unit in progress and the next path of it
     unsigned unit_x0 = 0, unit_y0 = 0, unit_s0 = 0, unit_ns = 0, unit_next = 0, unit_size = 0;
     bool exhausted = false;  // the global unit counter has run past n_units
-    unsigned wait_base = 0;  // lanes that were still waiting after the last service
+    int walk_min = 0;  // the node phase runs while more than walk_min lanes stand on an inner node
     unsigned nseg = 0;
     TraceCounters tc;
     tc.nodes = 0; tc.prims = 0;
 
     for (;;) {
-        const bool inner = st == ST_TRAV && PT_IS_INNER(T.cur);
-        const unsigned m_inner = __ballot_sync(0xffffffffu, inner);
-        if (m_inner != 0u && (unsigned)__popc(~m_inner) < wait_base + (unsigned)serve_min) {
-            if (inner) node_step<COUNT>(sv, T, stack, tc);
+        // invariant: T.cur == PT_SENTINEL unless st == ST_TRAV, so the vote only looks at T.cur
+        const bool inner = PT_IS_INNER(T.cur);
+        const int n_inner = __popc(__ballot_sync(0xffffffffu, inner));
+        if (n_inner > walk_min) {
+            if (inner) {
+                node_step<COUNT>(sv, T, stack, tc);
+                if (n_inner > walk_min + 4 && PT_IS_INNER(T.cur))  // a second step on the same vote (the vote costs ~1/4 of a step) node_step<COUNT>(sv, T, stack, tc);
+            }
             continue;
         }
         // ---- service ---------------------------------------------------------------------------------
-        if (st == ST_TRAV && T.cur < 0) leaf_step<COUNT>(sv, p.o, p.d, rc.tmin, T, stack, tc);
+        if (T.cur < 0) leaf_step<COUNT>(sv, p.o, p.d, rc.tmin, T, stack, tc);
         __syncwarp();
         const unsigned m_fin = __ballot_sync(0xffffffffu, st == ST_TRAV && T.cur == PT_SENTINEL);
         const unsigned m_idle = __ballot_sync(0xffffffffu, st == ST_IDLE);
@@ -142,10 +146,9 @@ k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* _
             }
             __syncwarp();
         }
-        const unsigned m_wait = __ballot_sync(0xffffffffu, !(st == ST_TRAV && PT_IS_INNER(T.cur)));
-        if (m_wait == 0xffffffffu && __ballot_sync(0xffffffffu, st != ST_DEAD) == 0u) break;  // every lane is dead
+        if (__ballot_sync(0xffffffffu, st != ST_DEAD) == 0u) break;  // every lane is dead
         // lanes that still wait (finished but not yet shaded, dead) do not count towards the next trigger
-        wait_base = __popc(__ballot_sync(0xffffffffu, st != ST_TRAV || T.cur == PT_SENTINEL));
+        walk_min = max(0, __popc(__ballot_sync(0xffffffffu, T.cur != PT_SENTINEL)) - serve_min);
     }
     nseg += __shfl_xor_sync(0xffffffffu, nseg, 16);
     nseg += __shfl_xor_sync(0xffffffffu, nseg, 8);
@@ -178,18 +181,21 @@ k_trace_persist(const SceneView sv, const float4* __restrict__ rays, const unsig
     T.cur = PT_SENTINEL; T.sp = 1;
     int st = ST_IDLE;
     bool exhausted = false;
-    unsigned wait_base = 0;
+    int walk_min = 0;
     TraceCounters tc;
     tc.nodes = 0; tc.prims = 0;
     for (;;) {
-        const bool inner = st == ST_TRAV && PT_IS_INNER(T.cur);
-        const unsigned m_inner = __ballot_sync(0xffffffffu, inner);
-        if (m_inner != 0u && (unsigned)__popc(~m_inner) < wait_base + (unsigned)serve_min) {
-            if (inner) node_step<COUNT>(sv, T, stack, tc);
+        const bool inner = PT_IS_INNER(T.cur);  // T.cur == PT_SENTINEL unless st == ST_TRAV
+        const int n_inner = __popc(__ballot_sync(0xffffffffu, inner));
+        if (n_inner > walk_min) {
+            if (inner) {
+                node_step<COUNT>(sv, T, stack, tc);
+                if (n_inner > walk_min + 4 && PT_IS_INNER(T.cur))  // a second step on the same vote (the vote costs ~1/4 of a step) node_step<COUNT>(sv, T, stack, tc);
+            }
             continue;
         }
         // ---- service: leaves, then results + refill ------------------------------------------------------
-        if (st == ST_TRAV && T.cur < 0) leaf_step<COUNT>(sv, o, d, tmin, T, stack, tc);
+        if (T.cur < 0) leaf_step<COUNT>(sv, o, d, tmin, T, stack, tc);
         __syncwarp();
         const unsigned m_fin = __ballot_sync(0xffffffffu, st == ST_TRAV && T.cur == PT_SENTINEL);
         const unsigned m_idle = __ballot_sync(0xffffffffu, st == ST_IDLE);
@@ -224,7 +230,7 @@ k_trace_persist(const SceneView sv, const float4* __restrict__ rays, const unsig
             __syncwarp();
         }
         if (__ballot_sync(0xffffffffu, st != ST_DEAD) == 0u) break;
-        wait_base = __popc(__ballot_sync(0xffffffffu, st != ST_TRAV || T.cur == PT_SENTINEL));
+        walk_min = max(0, __popc(__ballot_sync(0xffffffffu, T.cur != PT_SENTINEL)) - serve_min);
     }
     if (COUNT) {
         atomicAdd(&counters[CNT_NODES], (unsigned long long)tc.nodes);
