@@ -67,7 +67,8 @@ k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* _
         if (n_inner > walk_min) {
             if (inner) {
                 node_step<COUNT>(sv, T, stack, tc);
-                if (n_inner > walk_min + 4 && PT_IS_INNER(T.cur))  // a second step on the same vote (the vote costs ~1/4 of a step) node_step<COUNT>(sv, T, stack, tc);
+                // a second step on the same vote (the vote costs about a quarter of a step)
+                if (n_inner > walk_min + 4 && PT_IS_INNER(T.cur)) node_step<COUNT>(sv, T, stack, tc);
             }
             continue;
         }
@@ -190,7 +191,8 @@ k_trace_persist(const SceneView sv, const float4* __restrict__ rays, const unsig
         if (n_inner > walk_min) {
             if (inner) {
                 node_step<COUNT>(sv, T, stack, tc);
-                if (n_inner > walk_min + 4 && PT_IS_INNER(T.cur))  // a second step on the same vote (the vote costs ~1/4 of a step) node_step<COUNT>(sv, T, stack, tc);
+                // a second step on the same vote (the vote costs about a quarter of a step)
+                if (n_inner > walk_min + 4 && PT_IS_INNER(T.cur)) node_step<COUNT>(sv, T, stack, tc);
             }
             continue;
         }
