@@ -131,7 +131,7 @@ def cpu_baseline_run(world, cam, W, H, depth, target_seconds, threads=0, model=0
     t0 = time.perf_counter()
     O.render(sc, cs, W, H, 1, depth, model, seed=1, threads=threads)
     t1 = time.perf_counter() - t0
-    spp = int(max(1, min(64, target_seconds / max(t1, 1e-3))))
+    spp = int(max(1, min(1024, target_seconds / max(t1, 1e-3))))
     t0 = time.perf_counter()
     _, _, st = O.render(sc, cs, W, H, spp, depth, model, seed=1, threads=threads)
     dt = time.perf_counter() - t0
@@ -273,8 +273,9 @@ def run_ours(args):
         ms_sh = float(sum(s.ms_shade for s in stats))
         n_ext = int(sum(s.launches_extend for s in stats))
         n_sh = int(sum(s.launches_shade for s in stats))
-        if n_ext == 0:  # fused wavefront: one kernel runs extend + shade + regeneration + compaction
-            kname, bytes_k, ms_k, n_k = "k_paths", 160.0 * seg_rank0 + B_PER_PATH * paths_rank0, ms_sh, n_sh
+        if n_ext == 0:  # fused wavefront / persistent kernel: one kernel runs extend + shade + regeneration
+            kname = "k_paths_persist" if int(stats[0].reserved[0]) == 3 else "k_paths"
+            bytes_k, ms_k, n_k = 160.0 * seg_rank0 + B_PER_PATH * paths_rank0, ms_sh, n_sh
         elif ms_sh >= ms_ext:
             kname, bytes_k, ms_k, n_k = "k_shade", B_SHADE_SEG * seg_rank0 + B_PER_PATH * paths_rank0, ms_sh, n_sh
         else:
@@ -285,6 +286,22 @@ def run_ours(args):
             fp32_peak = ctx.measure_fp32_peak()
         except Exception:
             fp32_peak = None
+        # one extra untimed render with the counting kernel variant: BVH nodes visited / primitives tested per segment
+        r.clear()
+        stc = r.render(scene, cs, spp, depth, model, seed=1, spp_offset=rank * spp, flags=L.PT_FLAG_COUNTERS, mode=args.mode,
+                       pool_capacity=args.pool, segments_per_launch=args.k, shade_min=args.shade_min, serve_min=args.serve_min)
+        nodes_seg = stc.nodes_visited / max(stc.segments, 1)
+        prims_seg = stc.prims_tested / max(stc.segments, 1)
+        # SURVEY 8d FP32 accounting: two child-box slab tests per BVH2 node (18 flop each), 17 flop per sphere test
+        # (45 per Moller-Trumbore triangle test), ~280 flop of shading per segment (transcendentals counted as 1)
+        flop_prim = 45.0 if model == L.PT_SHADE_LEGACY else 17.0
+        flops_seg = nodes_seg * 36.0 + prims_seg * flop_prim + 280.0
+        fp32_achieved = seg_rank0 * flops_seg / (t_local * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(f"{args.workload}:{kname}")
         cpu = cpu_baseline_run(world, cam, W, H, depth, 0.5 if args.no_cpu else 12.0, model=model)
         line = {
             "metric": "Mpaths/s", "value": paths_total / (t_max * 1e-3) / 1e6, "unit": "Mpaths/s",
@@ -299,12 +316,18 @@ def run_ours(args):
             "gpu_launches": int(sum(s.launches for s in stats)),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                         "frac": achieved / peak, "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                         "traffic_source": traffic["source"] if traffic else None, "peak_kind": peak_kind,
                          "launches": n_k, "avg_launch_ms": ms_k / max(n_k, 1),
+                         "algorithmic_bytes_per_launch": bytes_k / max(n_k, 1),
                          "algorithmic_bytes": "160 B/segment + 24 B/path for the whole wavefront step (k_paths); split mode: k_shade 112 B/segment + 24 B/path, k_extend 48 B/segment (SURVEY 8d)",
                          "whole_render_160B_per_segment": {"achieved": whole, "frac": whole / peak},
                          "kernel_ms": {"k_extend": ms_ext / K, "k_shade": ms_sh / K, "step": t_local / K}},
             "fp32_peak_tflops_measured": fp32_peak,
+            "roofline_fp32": {"bound": "fp32", "achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                              "frac": (fp32_achieved / fp32_peak) if fp32_peak else None,
+                              "flops_per_segment": flops_seg, "nodes_per_segment": nodes_seg, "prims_per_segment": prims_seg,
+                              "accounting": "36 flop per BVH2 node visit + 17 per sphere / 45 per triangle test + 280 shading (SURVEY 8d)"},
             "cpu_baseline": {"value": cpu["mpaths"], "unit": "Mpaths/s", "cores": cpu["cores"], "kind": "port",
                              "sample": f"{W}x{H}, {cpu['spp']} spp, depth {depth}, {cpu['seconds']:.1f} s of OpenMP C "
                                        f"oracle (reference algorithm: " + ("unpruned stack walk of the stored SAH tree, "
@@ -370,13 +393,14 @@ def run_intersect(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_max = float(tt.item())
     st = ctx.trace_batch_device(sc, my.data_ptr(), n_local, hits.data_ptr(), L.PT_FLAG_COUNTERS | args.trace_flags)
+    st_plain = ctx.trace_batch_device(sc, my.data_ptr(), n_local, hits.data_ptr(), args.trace_flags)  # sort / traversal split
     # e2e: host ray buffer in, host ids/t out (pt_trace_batch), on a bounded slice
     n_e = min(n_local, 4 * 2**20)
     rays_h = my[:2 * n_e].cpu().numpy().reshape(n_e, 8)
     te = []
     for i in range(3):
         t0 = time.perf_counter()
-        ids_h, t_h, _ = ctx.trace_batch(sc, rays_h)
+        ids_h, t_h, _ = ctx.trace_batch(sc, rays_h)  # no counters: the plain kernel variant, no per-chunk sync
         te.append(time.perf_counter() - t0)
     if rank == 0:
         peak, peak_kind = measured_peaks()
@@ -385,6 +409,12 @@ def run_intersect(args):
         tris_per_ray = st.prims_tested / n_local
         bytes_per_ray = 32 + 8 + 64 * nodes_per_ray + 48 * tris_per_ray
         achieved = bytes_per_ray * n_local * K / (t_local * 1e-3) / 1e9
+        kname = "k_trace" if (args.trace_flags & L.PT_FLAG_TRACE_SIMPLE) else "k_trace_persist"
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(f"{args.workload}:{kname}")
         # CPU baseline: the oracle walking the SAME LBVH with the reference triangle test, bounded ray sample
         n_c = 2**18
         nodes, _ = sc.bvh_download()
@@ -405,8 +435,11 @@ def run_intersect(args):
             "e2e": {"value": n_e / min(te) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(n_e * 32),
                     "d2h_bytes_per_step": int(n_e * 16)},
             "gpu_launches": K, "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                         "traffic_source": traffic["source"] if traffic else None, "peak_kind": peak_kind,
+                         "step_ms": {"ray_sort": st_plain.ms_other, "traversal": st_plain.ms_extend, "step": t_local / K},
+                         "algorithmic_bytes_per_launch": bytes_per_ray * n_local,
                          "algorithmic_bytes": f"32 + 8 + 64*{nodes_per_ray:.1f} nodes + 48*{tris_per_ray:.2f} triangles "
                                               f"= {bytes_per_ray:.0f} B/ray (SURVEY 8d; counts from a counter-instrumented run)",
                          "compulsory_40B_per_ray": {"achieved": 40.0 * n_local * K / (t_local * 1e-3) / 1e9}},

@@ -197,9 +197,9 @@ class Context:
         n = rays.shape[0]
         ids = np.empty(n, np.int32)
         t = np.empty(n, np.float32)
-        st = PtStats()
+        st = PtStats()  # filled (and the counting kernel variant used) only when counters=True
         check(self.lib.pt_trace_batch(self.handle, scene.handle, _fptr(rays), n, _fptr(ids, np.int32), _fptr(t),
-                                      C.byref(st)))
+                                      C.byref(st) if counters else None))
         return ids, t, st
 
     def trace_batch_device(self, scene: "Scene", rays_ptr: int, n: int, hits_ptr: int, flags: int = 0) -> PtStats:

@@ -55,6 +55,13 @@ extern "C" void pt_context_destroy(PtContext* c) {
     if (c->hits) cudaFree(c->hits);
     if (c->scratch) cudaFree(c->scratch);
     if (c->sort_scratch) cudaFree(c->sort_scratch);
+    for (int b = 0; b < 2; ++b) {
+        if (c->stage_rays_h[b]) cudaFreeHost(c->stage_rays_h[b]);
+        if (c->stage_hits_h[b]) cudaFreeHost(c->stage_hits_h[b]);
+        if (c->stage_rays_d[b]) cudaFree(c->stage_rays_d[b]);
+        if (c->stage_hits_d[b]) cudaFree(c->stage_hits_d[b]);
+        if (c->stage_ev[b]) cudaEventDestroy(c->stage_ev[b]);
+    }
     if (c->counters) cudaFree(c->counters);
     if (c->counters_host) cudaFreeHost(c->counters_host);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
@@ -537,35 +544,81 @@ extern "C" int pt_scene_triangles_download(const PtScene* s, float* tris, int64_
 }
 
 // ---- host-buffer wrappers ----------------------------------------------------------------------
-extern "C" int pt_trace_batch(PtContext* ctx, const PtScene* s, const float* rays_host, int64_t n, int32_t* prim_id_host,
-                              float* t_host, PtStats* stats) {
-    PT_REQUIRE(ctx && s && n >= 0 && (n == 0 || (rays_host && prim_id_host && t_host)), "bad argument");
-    if (n == 0) {
-        if (stats) memset(stats, 0, sizeof *stats);
-        return PT_OK;
+// pt_trace_batch: host rays in, host ids/t out.  The batch is cut into chunks that go through a
+// double-buffered pipeline — CPU copies chunk k into pinned memory, the stream does H2D + trace + D2H
+// for it, and meanwhile the CPU unpacks the hit records of chunk k-1 — so pageable caller memory never
+// meets cudaMemcpy directly and nothing is allocated per call (grow-only staging in the context).
+static int ensure_trace_staging(PtContext* ctx, int64_t chunk) {
+    if (ctx->stage_chunk >= chunk) return PT_OK;
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->stage_rays_h[b]) cudaFreeHost(ctx->stage_rays_h[b]);
+        if (ctx->stage_hits_h[b]) cudaFreeHost(ctx->stage_hits_h[b]);
+        if (ctx->stage_rays_d[b]) cudaFree(ctx->stage_rays_d[b]);
+        if (ctx->stage_hits_d[b]) cudaFree(ctx->stage_hits_d[b]);
+        ctx->stage_rays_h[b] = ctx->stage_hits_h[b] = nullptr;
+        ctx->stage_rays_d[b] = ctx->stage_hits_d[b] = nullptr;
     }
-    PT_CUDA(cudaSetDevice(ctx->device));
-    float4 *d_rays = nullptr, *d_hits = nullptr;
-    PT_CUDA(cudaMalloc(&d_rays, (size_t)n * 2 * sizeof(float4)));
-    cudaError_t e = cudaMalloc(&d_hits, (size_t)n * sizeof(float4));
-    int rc = PT_OK;
-    std::vector<float4> hits;
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays_host, (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) rc = pt_trace_batch_device(ctx, s, d_rays, n, d_hits, stats ? PT_FLAG_COUNTERS : 0, stats);
-    if (e == cudaSuccess && rc == PT_OK) {
-        hits.resize((size_t)n);
-        e = cudaMemcpyAsync(hits.data(), d_hits, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    ctx->stage_chunk = 0;
+    for (int b = 0; b < 2; ++b) {
+        PT_CUDA(cudaMallocHost(&ctx->stage_rays_h[b], (size_t)chunk * 32));
+        PT_CUDA(cudaMallocHost(&ctx->stage_hits_h[b], (size_t)chunk * 16));
+        PT_CUDA(cudaMalloc(&ctx->stage_rays_d[b], (size_t)chunk * 32));
+        PT_CUDA(cudaMalloc(&ctx->stage_hits_d[b], (size_t)chunk * 16));
+        if (!ctx->stage_ev[b]) PT_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[b], cudaEventDisableTiming));
     }
-    cudaFree(d_rays);
-    if (d_hits) cudaFree(d_hits);
-    PT_CUDA(e);
-    if (rc) return rc;
+    ctx->stage_chunk = chunk;
+    return PT_OK;
+}
+
+static void unpack_hits(const float4* hits, int64_t n, int32_t* prim_id, float* t) {
     for (int64_t k = 0; k < n; ++k) {
         int id;
         memcpy(&id, &hits[k].y, 4);
-        prim_id_host[k] = id;
-        t_host[k] = id >= 0 ? hits[k].x : -1.0f;
+        prim_id[k] = id;
+        t[k] = id >= 0 ? hits[k].x : -1.0f;
     }
+}
+
+extern "C" int pt_trace_batch(PtContext* ctx, const PtScene* s, const float* rays_host, int64_t n, int32_t* prim_id_host,
+                              float* t_host, PtStats* stats) {
+    PT_REQUIRE(ctx && s && n >= 0 && (n == 0 || (rays_host && prim_id_host && t_host)), "bad argument");
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (n == 0) return PT_OK;
+    if (!s->built) { pt_set_error("pt_trace_batch: scene not built"); return PT_ERR_NOT_BUILT; }
+    PT_CUDA(cudaSetDevice(ctx->device));
+    const int64_t CHUNK = (int64_t)1 << 20;
+    const int64_t chunk = n < CHUNK ? n : CHUNK;
+    int rc = ensure_trace_staging(ctx, chunk);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    const int64_t n_chunks = (n + chunk - 1) / chunk;
+    for (int64_t k = 0; k <= n_chunks; ++k) {
+        const int b = (int)(k & 1);
+        if (k < n_chunks) {
+            const int64_t lo = k * chunk, cnt = (lo + chunk <= n ? chunk : n - lo);
+            // buffer b was last used by chunk k-2, whose results were unpacked in iteration k-1
+            memcpy(ctx->stage_rays_h[b], rays_host + 8 * lo, (size_t)cnt * 32);
+            PT_CUDA(cudaMemcpyAsync(ctx->stage_rays_d[b], ctx->stage_rays_h[b], (size_t)cnt * 32, cudaMemcpyHostToDevice, st));
+            PtStats cs;
+            rc = pt_trace_batch_device(ctx, s, ctx->stage_rays_d[b], cnt, ctx->stage_hits_d[b], stats ? PT_FLAG_COUNTERS : 0,
+                                       stats ? &cs : nullptr);
+            if (rc) return rc;
+            if (stats) {
+                stats->paths += cs.paths; stats->segments += cs.segments;
+                stats->nodes_visited += cs.nodes_visited; stats->prims_tested += cs.prims_tested;
+                stats->ms_total += cs.ms_total; stats->ms_extend += cs.ms_extend;
+                stats->launches += cs.launches; stats->launches_extend += cs.launches_extend;
+            }
+            PT_CUDA(cudaMemcpyAsync(ctx->stage_hits_h[b], ctx->stage_hits_d[b], (size_t)cnt * 16, cudaMemcpyDeviceToHost, st));
+            PT_CUDA(cudaEventRecord(ctx->stage_ev[b], st));
+        }
+        if (k >= 1) {  // unpack chunk k-1 while the GPU works on chunk k
+            const int pb = (int)((k - 1) & 1);
+            const int64_t lo = (k - 1) * chunk, cnt = (lo + chunk <= n ? chunk : n - lo);
+            PT_CUDA(cudaEventSynchronize(ctx->stage_ev[pb]));
+            unpack_hits((const float4*)ctx->stage_hits_h[pb], cnt, prim_id_host + lo, t_host + lo);
+        }
+    }
+    PT_CUDA(cudaGetLastError());
     return PT_OK;
 }

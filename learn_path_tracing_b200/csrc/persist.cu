@@ -305,10 +305,9 @@ static int resident_blocks(PtContext* ctx, K kernel, int* out) {
 }
 
 int pt_trace_persist(PtContext* ctx, const PtScene* s, const float4* rays, long long n, float4* hits, bool count,
-                     bool sort, int serve_min, int fetch_min, float* ms_sort) {
+                     bool sort, int serve_min, int fetch_min, cudaEvent_t ev_sorted) {
     cudaStream_t st = ctx->stream;
     const unsigned* order = nullptr;
-    if (ms_sort) *ms_sort = 0.0f;
     if (sort && n > 1) {
         PT_REQUIRE(n < (1ll << 32), "ray batches are limited to 2^32 - 1 rays");
         size_t tmp_bytes = 0;
@@ -328,6 +327,7 @@ int pt_trace_persist(PtContext* ctx, const PtScene* s, const float4* rays, long 
         PT_CUDA(cub::DeviceRadixSort::SortPairs(base + 4 * arr, tmp_bytes, kb, vb, (int)n, 0, 30, st));
         order = vb.Current();
     }
+    if (ev_sorted) PT_CUDA(cudaEventRecord(ev_sorted, st));
     int blocks = 0, rcb;
     if (count) rcb = resident_blocks(ctx, k_trace_persist<true>, &blocks);
     else rcb = resident_blocks(ctx, k_trace_persist<false>, &blocks);

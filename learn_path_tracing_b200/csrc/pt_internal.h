@@ -78,6 +78,11 @@ struct PtContext {
     // grow-only device scratch of the ray sort (keys, order, cub temporaries)
     void* sort_scratch = nullptr;
     size_t sort_bytes = 0;
+    // pt_trace_batch (host buffers): double-buffered pinned + device staging, `stage_chunk` rays each
+    int64_t stage_chunk = 0;
+    void *stage_rays_h[2] = {nullptr, nullptr}, *stage_hits_h[2] = {nullptr, nullptr};
+    void *stage_rays_d[2] = {nullptr, nullptr}, *stage_hits_d[2] = {nullptr, nullptr};
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
 };
 
 struct HostMesh {
@@ -143,6 +148,6 @@ struct RenderConsts;
 int pt_render_persist(PtContext* ctx, const PtScene* s, const RenderConsts& rc, bool legacy, bool count, float4* accum,
                       float4* accum_sq, int shade_min, int serve_min);
 int pt_trace_persist(PtContext* ctx, const PtScene* s, const float4* rays, long long n, float4* hits, bool count,
-                     bool sort, int serve_min, int fetch_min, float* ms_sort);
+                     bool sort, int serve_min, int fetch_min, cudaEvent_t ev_sorted);
 // post.cu
 int pt_ensure_scratch(PtContext* ctx, size_t bytes);

@@ -559,6 +559,7 @@ extern "C" int pt_trace_batch_device(PtContext* ctx, const PtScene* s, const voi
     if (rcp) return rcp;
     cudaStream_t st = ctx->stream;
     const bool count = (flags & PT_FLAG_COUNTERS) != 0;
+    bool persist = false;
     PT_CUDA(cudaMemsetAsync(ctx->counters, 0, CNT_WORDS * sizeof(unsigned long long), st));
     PT_CUDA(cudaEventRecord(ctx->ev_a, st));
     if (n > 0) {
@@ -570,8 +571,9 @@ extern "C" int pt_trace_batch_device(PtContext* ctx, const PtScene* s, const voi
             const bool sort = !(flags & PT_FLAG_NO_SORT) && n >= (1 << 16);
             const int serve_min = (flags >> 8) & 63, fetch_min = (flags >> 14) & 63;
             int rct = pt_trace_persist(ctx, s, (const float4*)rays_dev, n, (float4*)hits_dev, count, sort,
-                                       serve_min ? serve_min : 8, fetch_min ? fetch_min : 8, nullptr);
+                                       serve_min ? serve_min : 8, fetch_min ? fetch_min : 8, stats ? get_event(ctx, 0) : nullptr);
             if (rct) return rct;
+            persist = true;
         }
     }
     PT_CUDA(cudaEventRecord(ctx->ev_b, st));
@@ -587,6 +589,10 @@ extern "C" int pt_trace_batch_device(PtContext* ctx, const PtScene* s, const voi
         stats->prims_tested = last[CNT_PRIMS];
         cudaEventElapsedTime(&stats->ms_total, ctx->ev_a, ctx->ev_b);
         stats->ms_extend = stats->ms_total;
+        if (persist) {  // ms_other = ray keys + radix sort, ms_extend = the traversal kernel alone
+            cudaEventElapsedTime(&stats->ms_other, ctx->ev_a, ctx->ev_pool[0]);
+            cudaEventElapsedTime(&stats->ms_extend, ctx->ev_pool[0], ctx->ev_b);
+        }
         stats->launches = n > 0 ? 1 : 0;
         stats->launches_extend = stats->launches;
     }

@@ -177,7 +177,7 @@ def test_random_triangles_match_bruteforce_oracle(ctx, oracle):
     sc = L.Scene(ctx)
     sc.set_triangles(tris)
     sc.build()
-    gid, gt, st = ctx.trace_batch(sc, rays)
+    gid, gt, st = ctx.trace_batch(sc, rays, counters=True)
     oid, ot, ot2 = oracle.trace_triangles(tris, rays, want_second=True)
     agree = gid == oid
     # disagreements must be explainable as ties or edge grazes
