@@ -100,7 +100,7 @@ typedef struct PtRenderParams {
     float absorptivity;     /* legacy only: 0.25 (15_module.py:893,950) or 0.5 (14_mesh.py:833,889) */
     int32_t pool_capacity;  /* path-pool slots; 0 = library default                                 */
     int32_t flags;          /* PT_FLAG_*                                                            */
-    int32_t reserved[6];    /* [0] wavefront mode: 0 auto (3 when the scene has a BVH, else 2), 1 split (k_extend +
+    int32_t reserved[6];    /* [0] wavefront mode: 0 auto (= 3), 1 split (k_extend +
                                    k_shade per bounce), 2 fused K-step (k_paths), 3 persistent while-while (k_paths_persist)
                                [1] fused mode: ray segments per path slot per launch (0 = default 32)
                                [2] persistent mode: finished lanes that trigger shading + refill (0 = default 12)

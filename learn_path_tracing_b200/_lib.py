@@ -24,8 +24,8 @@ PT_FLAG_COUNTERS = 4
 
 PT_MODE_AUTO = 0
 PT_MODE_SPLIT = 1   # classic wavefront: k_extend + k_shade per bounce, pool refilled by an atomic counter
-PT_MODE_FUSED = 2   # k_paths: K segments per launch in registers, compaction at write-back (auto for tree-less scenes)
-PT_MODE_PERSIST = 3  # k_paths_persist: persistent while-while lanes, one launch per render (auto for scenes with a BVH)
+PT_MODE_FUSED = 2   # k_paths: K segments per launch in registers, compaction at write-back (the HBM path-pool wavefront)
+PT_MODE_PERSIST = 3  # k_paths_persist: persistent while-while lanes, one launch per render (auto)
 PT_FLAG_NO_SORT = 8        # pt_trace_batch_device: keep batch order
 PT_FLAG_TRACE_SIMPLE = 16  # pt_trace_batch_device: one ray per thread (k_trace)
 
