@@ -16,12 +16,15 @@ struct Hit {
 // to the CPU oracle.  The reference's b = 2*oc.rd, disc = b*b - 4c, t = (-b -+ sqrt(disc))/2 is written
 // in the half-b form, which is exactly equal in binary floating point (scaling by 2 and 4 is exact).
 // Returns false when the discriminant is negative (reference leaves t = -1).
-PT_DEV bool sphere_hit_ref(float3 o, float3 d, float4 cr, float r2, bool transparent, float* t_out) {
+PT_DEV bool sphere_hit_ref(float3 o, float3 d, float4 cr, float r2, bool transparent, float tmin, float* t_out) {
     float ocx = __fsub_rn(o.x, cr.x), ocy = __fsub_rn(o.y, cr.y), ocz = __fsub_rn(o.z, cr.z);
     float h = __fadd_rn(__fadd_rn(__fmul_rn(ocx, d.x), __fmul_rn(ocy, d.y)), __fmul_rn(ocz, d.z));
     float c = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(ocx, ocx), __fmul_rn(ocy, ocy)), __fmul_rn(ocz, ocz)), r2);
     float disc = __fsub_rn(__fmul_rn(h, h), c);
     if (!(disc >= 0.0f)) return false;
+    // both roots lie behind tmin when -h does (the near root is -h - s <= -h; the far root is only taken by
+    // transparent spheres): such a hit is rejected by every caller (t >= tmin), so the square root is skipped
+    if (!transparent && -h < tmin) { *t_out = -INFINITY; return true; }
     float s = __fsqrt_rn(disc);
     float t = __fsub_rn(-h, s);
     if (t < PT_EPS && transparent) t = __fadd_rn(-h, s);  // world.py:55-56 far-root rule
@@ -58,7 +61,7 @@ PT_DEV void test_prim(const SceneView& sv, int p, float3 o, float3 d, float tmin
     if (p < sv.n_sph) {
         float4 cr = __ldg(&sv.sph_cr[p]);
         float4 aux = __ldg(&sv.sph_aux[p]);
-        ok = sphere_hit_ref(o, d, cr, aux.x, __float_as_int(aux.y) != 0, &t);
+        ok = sphere_hit_ref(o, d, cr, aux.x, __float_as_int(aux.y) != 0, tmin, &t);
     } else {
         const float4* g = sv.tri_geo + 3 * (size_t)(p - sv.n_sph);
         float4 v0 = __ldg(g), e1 = __ldg(g + 1), e2 = __ldg(g + 2);
@@ -85,7 +88,7 @@ PT_DEV Hit closest_hit(const SceneView& sv, float3 o, float3 d, float tmin, floa
             if (COUNT) tc.prims++;
             float t;
             const int p = sv.inl_id[g];
-            if (sphere_hit_ref(o, d, sv.inl_cr[g], sv.inl_r2[g], sv.inl_transparent[g] != 0, &t) && t >= tmin &&
+            if (sphere_hit_ref(o, d, sv.inl_cr[g], sv.inl_r2[g], sv.inl_transparent[g] != 0, tmin, &t) && t >= tmin &&
                 (t < best || (t == best && p < h.prim))) {
                 best = t;
                 h.t = t; h.prim = p;
@@ -169,20 +172,21 @@ PT_DEV void trav_begin(const SceneView& sv, float3 o, float3 d, float tmin, floa
         if (COUNT) tc.prims++;
         float t;
         const int p = sv.inl_id[g];
-        if (sphere_hit_ref(o, d, sv.inl_cr[g], sv.inl_r2[g], sv.inl_transparent[g] != 0, &t) && t >= tmin &&
+        if (sphere_hit_ref(o, d, sv.inl_cr[g], sv.inl_r2[g], sv.inl_transparent[g] != 0, tmin, &t) && t >= tmin &&
             (t < T.best || (t == T.best && p < T.h.prim))) {
             T.best = t;
             T.h.t = t; T.h.prim = p;
         }
     }
     for (int g = 0; g < sv.n_global; ++g) test_prim<COUNT>(sv, __ldg(&sv.global_prims[g]), o, d, tmin, T.h, T.best, tc);
+    T.cur = sv.root;
+    if (T.cur == PT_SENTINEL) return;  // tree-less scene (<= 8 primitives): the inline / global tests were everything
     T.inv = f3(1.0f / (fabsf(d.x) < 1e-18f ? copysignf(1e-18f, d.x) : d.x),
                1.0f / (fabsf(d.y) < 1e-18f ? copysignf(1e-18f, d.y) : d.y),
                1.0f / (fabsf(d.z) < 1e-18f ? copysignf(1e-18f, d.z) : d.z));
     T.oi = f3(-o.x * T.inv.x, -o.y * T.inv.y, -o.z * T.inv.z);
     stack[0] = PT_SENTINEL;
     T.sp = 1;
-    T.cur = sv.root;
     if (T.cur < 0) {  // degenerate tree: the root is a leaf
         test_prim<COUNT>(sv, ~T.cur, o, d, tmin, T.h, T.best, tc);
         T.cur = PT_SENTINEL;
