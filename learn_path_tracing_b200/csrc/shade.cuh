@@ -107,10 +107,15 @@ PT_DEV float3 sky_color(float3 d) {  // backbround_color, __main__.py:58-62
 }
 
 // ---- legacy textures ------------------------------------------------------------------------
-PT_DEV int pymod(int a, int m) {  // ti.mod: Python modulo
-    if (m > 0 && a >= -m && a < 2 * m) return a < 0 ? a + m : (a >= m ? a - m : a);  // the usual case: no division
-    int r = a % m;
-    return (r != 0 && ((r < 0) != (m < 0))) ? r + m : r;
+// ti.mod (Python modulo) by the area width w > 0, without an integer division: floor(a / w) from the float
+// reciprocal is off by at most one for |a| < 2^23 (texture coordinates that tile many times still are), and the
+// remainder is corrected by one step.  Tiling uvs (ground plane) made the generic a % m a hot spot.
+PT_DEV int pymod_w(int a, int w, float inv_w) {
+    const int q = __float2int_rd((float)a * inv_w);
+    int r = a - q * w;
+    if (r < 0) r += w;
+    else if (r >= w) r -= w;
+    return r;
 }
 
 struct Taps {
@@ -128,10 +133,12 @@ PT_DEV Taps bilinear_taps(int4 area, float u, float v) {
     k.lt = ((float)r - u) * (v - (float)b);
     k.rb = (u - (float)l) * ((float)t - v);
     k.rt = (u - (float)l) * (v - (float)b);
-    k.l = area.x + pymod(l, w);
-    k.r = area.x + pymod(r, w);
-    k.b = area.y + pymod(b, w);
-    k.t = area.y + pymod(t, w);
+    const float inv_w = 1.0f / (float)w;
+    const int ml = pymod_w(l, w, inv_w), mb = pymod_w(b, w, inv_w);  // (x + 1) mod w follows from x mod w
+    k.l = area.x + ml;
+    k.r = area.x + (ml + 1 >= w ? ml + 1 - w : ml + 1);
+    k.b = area.y + mb;
+    k.t = area.y + (mb + 1 >= w ? mb + 1 - w : mb + 1);
     return k;
 }
 
