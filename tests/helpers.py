@@ -86,3 +86,14 @@ def mesh_camera(resolution):
     cam.set_position(legacy.Vec3f([0, 8, -30]))
     cam.look_at(legacy.Vec3f([0, 8, 0]))
     return cam
+
+
+def hit_tolerance(tris, tri_ids, rays, t):
+    """|dt| bound for one (ray, triangle) pair: the contract's 1e-5 relative, plus the unavoidable rounding of f32
+    coordinates (a few ulps of the scene scale) amplified by 1/|d.N| when the ray grazes the triangle's plane."""
+    T = tris[np.maximum(tri_ids, 0)]
+    n = np.cross(T[:, 3:6] - T[:, 0:3], T[:, 6:9] - T[:, 0:3])
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    dn = np.abs((rays[:, 4:7] * n).sum(1))
+    scale = np.maximum(np.abs(rays[:, :3]).max(1), np.abs(T).max(1))
+    return 1e-5 * np.abs(t) + 16 * 1.2e-7 * scale / np.maximum(dn, 1e-12)
