@@ -6,15 +6,17 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
-from learn_path_tracing_b200 import DielectricBSDF, DiffuseBSDF, imwrite, render, scenes  # noqa: E402
+from learn_path_tracing_b200 import DielectricBSDF, DiffuseBSDF, NormalColor, imwrite, render, scenes  # noqa: E402
 
 
 def main(stage, resolution=(1280, 720), spp=8192, propagate_limit=32):
     spp = int(os.environ.get("LPT_SPP", spp))
     world, camera = scenes.SCENES[stage](resolution)
     start_time = time.time()
-    image, stats = render(world, camera, spp=spp, propagate_limit=propagate_limit,
-                          bsdf=DiffuseBSDF if stage == "6_diffuse" else DielectricBSDF, return_stats=True)
+    bsdf = {"5_anti_aliasing": NormalColor, "6_diffuse": DiffuseBSDF}.get(stage, DielectricBSDF)
+    # stage 5 writes the linear image (no post_processing() in that script)
+    image, stats = render(world, camera, spp=spp, propagate_limit=propagate_limit, bsdf=bsdf, return_stats=True,
+                          postprocess=stage != "5_anti_aliasing")
     print(f"Time elapsed: {time.time() - start_time:.2f}s  ({stats.paths / stats.ms_total / 1e3:.0f} Mpaths/s)")
     os.makedirs("outputs", exist_ok=True)
     imwrite(image, f"outputs/{stage}.png")

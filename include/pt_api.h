@@ -53,6 +53,8 @@ extern "C" {
 #define PT_SHADE_V2 0           /* taichi_pathtracer stages 7-10: MetalBSDF / DielectricBSDF (bsdf.py:71-110) */
 #define PT_SHADE_V2_DIFFUSE 1   /* taichi_pathtracer/6_diffuse: DiffuseBSDF only (6_diffuse/bsdf.py:20-26)     */
 #define PT_SHADE_LEGACY 2       /* legacy 14_mesh/15_module gen_secondary_rays (15_module.py:994-1013)         */
+#define PT_SHADE_V2_NORMALS 3   /* taichi_pathtracer stages 4-5: colour = 0.5 (normal + 1), no bounce (5_anti_aliasing/__main__.py:19-28);
+                                   persistent kernel only                                                      */
 
 /* PtRenderParams.flags */
 #define PT_FLAG_ACCUM_SQ 1      /* also accumulate per-pixel sum of squares (needs accum_sq != NULL)   */

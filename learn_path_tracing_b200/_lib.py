@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libb200pt.so")
 PT_SHADE_V2 = 0
 PT_SHADE_V2_DIFFUSE = 1
 PT_SHADE_LEGACY = 2
+PT_SHADE_V2_NORMALS = 3
 
 PT_FLAG_ACCUM_SQ = 1
 PT_FLAG_TIMING = 2

@@ -20,3 +20,8 @@ class MetalBSDF:
 class DielectricBSDF:
     """Schlick coin; albedo-tinted refraction / Lambert, else mirror — bsdf.py:89-110."""
     shading_model = _lib.PT_SHADE_V2
+
+
+class NormalColor:
+    """Stages 4-5 `ray_color`: 0.5 (normal + 1) on a hit, sky otherwise, no bounce — 5_anti_aliasing/__main__.py:19-28."""
+    shading_model = _lib.PT_SHADE_V2_NORMALS

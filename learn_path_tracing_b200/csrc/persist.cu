@@ -87,6 +87,12 @@ k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* _
                         if (rc.accum_sq) atomicAdd(&accum_sq[p.pixel], make_float4(c.x * c.x, c.y * c.y, c.z * c.z, 1.0f));
                     }
                     st = ST_IDLE;
+                } else if (!LEGACY && rc.shading_model == PT_SHADE_V2_NORMALS) {  // stages 4-5: normal as colour, no bounce
+                    T.h.t = T.best;
+                    const float3 c = normal_color(sv, p, T.h);
+                    atomicAdd(&accum[p.pixel], make_float4(c.x, c.y, c.z, 1.0f));
+                    if (rc.accum_sq) atomicAdd(&accum_sq[p.pixel], make_float4(c.x * c.x, c.y * c.y, c.z * c.z, 1.0f));
+                    st = ST_IDLE;
                 } else {
                     T.h.t = T.best;
                     if (LEGACY) scatter_legacy(sv, p, T.h, rc.absorptivity, rc.seed);

@@ -101,6 +101,13 @@ PT_DEV void scatter_v2(const SceneView& sv, PathState& p, const Hit& h, int shad
     }
 }
 
+// stages 4-5 (5_anti_aliasing/__main__.py:19-28): the outward geometric normal as a colour, path ends at the hit
+PT_DEV float3 normal_color(const SceneView& sv, const PathState& p, const Hit& h) {
+    const float4 cr = __ldg(&sv.sph_cr[h.prim]);
+    const float3 n = normalize(p.o + h.t * p.d - f3(cr));
+    return f3(0.5f * (n.x + 1.0f), 0.5f * (n.y + 1.0f), 0.5f * (n.z + 1.0f));
+}
+
 PT_DEV float3 sky_color(float3 d) {  // backbround_color, __main__.py:58-62
     float t = 0.5f * (d.y + 1.0f);
     return f3((1.0f - t) + t * 0.5f, (1.0f - t) + t * 0.7f, (1.0f - t) + t);

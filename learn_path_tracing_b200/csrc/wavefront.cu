@@ -438,7 +438,7 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
     PT_REQUIRE(p->max_depth > 0 && p->max_depth < 256, "max_depth must be in [1,255]");
     PT_REQUIRE((long long)p->spp_offset + p->spp <= (1 << 24), "sample index must stay below 2^24");
     PT_REQUIRE((long long)p->width * p->height < (1ll << 31), "image too large");
-    PT_REQUIRE(p->shading_model >= 0 && p->shading_model <= 2, "unknown shading model");
+    PT_REQUIRE(p->shading_model >= 0 && p->shading_model <= 3, "unknown shading model");
     const bool legacy = p->shading_model == PT_SHADE_LEGACY;
     PT_REQUIRE(legacy || (s->view.n_tri == 0 && !s->view.legacy_spheres), "v2 shading models need a v2 sphere scene");
     PT_REQUIRE(!legacy || s->view.n_sph == 0 || s->view.legacy_spheres, "legacy shading needs legacy (textured) spheres");
@@ -451,6 +451,7 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
     // auto: the persistent ballot-scheduled kernel (measured faster than the K-step fused wavefront on every
     // workload, tree-less scenes included: 16.3 vs 15.3 Gpaths/s on 8_refract 1080p)
     const int mode = p->reserved[0] != PT_MODE_AUTO ? p->reserved[0] : PT_MODE_PERSIST;
+    PT_REQUIRE(p->shading_model != PT_SHADE_V2_NORMALS || mode == PT_MODE_PERSIST, "PT_SHADE_V2_NORMALS needs the persistent kernel (mode 0 or 3)");
     PT_CUDA(cudaSetDevice(ctx->device));
 
     const unsigned long long total = (unsigned long long)p->width * p->height * (unsigned long long)p->spp;

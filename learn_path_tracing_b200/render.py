@@ -91,7 +91,7 @@ class Renderer:
 
 
 def render(world, camera, spp: int = 8192, propagate_limit: int = 32, seed: int = 1, bsdf=None,
-           ctx: _lib.Context | None = None, return_stats: bool = False):
+           ctx: _lib.Context | None = None, return_stats: bool = False, postprocess: bool = True):
     """Drop-in for the v2 scripts' render(world, camera) + post_processing(): returns the tonemapped
     image as a float32 [W,H,3] array in Taichi field layout (pass it to imwrite)."""
     ctx = ctx or default_context()
@@ -99,5 +99,5 @@ def render(world, camera, spp: int = 8192, propagate_limit: int = 32, seed: int 
     model = getattr(bsdf, "shading_model", _lib.PT_SHADE_V2)
     r = Renderer(w, h, ctx)
     st = r.render(world.device_scene(ctx), camera.to_struct(), spp, propagate_limit, model, seed)
-    img = r.image(aces=True, gamma=2.2)
+    img = r.image(aces=True, gamma=2.2) if postprocess else r.mean()  # stages <= 5 write the linear image
     return (img, st) if return_stats else img

@@ -24,6 +24,15 @@ def _six_spheres(with_glass=True, ground_y=-10000.5):
     return [s1, s2, s3, s4, s5, ground]
 
 
+def scene_5_anti_aliasing(resolution=(1280, 720)):
+    """5_anti_aliasing/__main__.py:44-50 (also 4_objects) — two plain spheres, normals shown as colours."""
+    w = World([Sphere(Vec3f([0.0, 0.0, 0.0]), 0.5), Sphere(Vec3f([0, -100.5, 0]), 100)])
+    cam = Camera(resolution)
+    cam.set_direction(0, 0)
+    cam.set_position(Vec3f([0, 0, 3]))
+    return w, cam
+
+
 def scene_6_diffuse(resolution=(1280, 720)):
     """6_diffuse/__main__.py:62-71 — Lambert-only spheres (albedo only)."""
     w = World([
@@ -98,5 +107,5 @@ def scene_10_final(resolution=(1280, 720), seed=20261018):
     return random_scene(seed=seed), cam
 
 
-SCENES = {"6_diffuse": scene_6_diffuse, "7_reflect": scene_7_reflect, "8_refract": scene_8_refract,
+SCENES = {"5_anti_aliasing": scene_5_anti_aliasing, "6_diffuse": scene_6_diffuse, "7_reflect": scene_7_reflect, "8_refract": scene_8_refract,
           "9_dof": scene_9_dof, "10_final": scene_10_final}

@@ -581,6 +581,11 @@ int orc_render(const OrcScene* sc, const PtCamera* cam, const PtRenderParams* p,
                             V3 point = vadd(ro, vscale(rd, t));                       /* world.py:57 */
                             V3 normal = vnormalized(vsub(point, vload(sc->sph_cr + 4 * id))); /* :58 */
                             float ior = m->ior;
+                            if (p->shading_model == PT_SHADE_V2_NORMALS) { /* 5_anti_aliasing/__main__.py:19-28 */
+                                radiance = v3(0.5f * (normal.x + 1.0f), 0.5f * (normal.y + 1.0f), 0.5f * (normal.z + 1.0f));
+                                ended = 1;
+                                break;
+                            }
                             if (vdot(rd, normal) > 0.0f) { /* world.py:31-33 */
                                 normal = vneg(normal);
                                 ior = 1.0f / ior;

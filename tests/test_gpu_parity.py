@@ -122,6 +122,27 @@ def test_image_within_3_sigma_of_oracle(ctx, oracle, name, model, depth, mode):
     assert abs(mu_g.mean() / mu_o.mean() - 1.0) < 2e-3
 
 
+def test_stage5_normals_match_oracle_and_reference_png(ctx, oracle):
+    """PT_SHADE_V2_NORMALS (stages 4-5): same paths as the oracle (sums equal to fp32 order) and the reference's own
+    outputs/5_anti_aliasing.png within silhouette noise."""
+    import os
+    from PIL import Image
+    from conftest import GOLDEN
+    W, H, SPP = 320, 180, 128
+    world, cam = scenes.scene_5_anti_aliasing((W, H))
+    r = L.Renderer(W, H, ctx)
+    st = r.render(world.device_scene(ctx), cam.to_struct(), SPP, 32, L.PT_SHADE_V2_NORMALS, seed=3)
+    osum, _, ost = oracle.render(oracle.scene_from_world(world), cam.to_struct(), W, H, SPP, 32, L.PT_SHADE_V2_NORMALS, seed=3)
+    assert st.paths == ost.paths and st.segments == st.paths == ost.segments
+    diff = np.abs(r.mean() - osum / SPP)   # same rays; a silhouette sample may flip hit/miss within float rounding
+    assert np.quantile(diff, 0.99) < 1e-4 and diff.max() < 3.0 / SPP, (np.quantile(diff, 0.99), diff.max())
+    gold = np.asarray(Image.open(os.path.join(GOLDEN, "5_anti_aliasing_320x180.png")).convert("RGB"), np.float64)
+    d = L.to_uint8(r.mean()).astype(np.float64) - gold
+    assert np.sqrt((d**2).mean()) < 1.5 and abs(d.mean()) < 0.3
+    with pytest.raises(L.PtError):  # only the persistent kernel implements this model
+        L.Renderer(W, H, ctx).render(world.device_scene(ctx), cam.to_struct(), 1, 32, L.PT_SHADE_V2_NORMALS, mode=L.PT_MODE_SPLIT)
+
+
 def test_fused_and_split_wavefronts_trace_the_same_paths(ctx):
     """Both wavefront forms key the RNG on (pixel, sample, bounce): same paths, images equal to summation order;
     small pools and short launches exercise regeneration, compaction and the tail."""

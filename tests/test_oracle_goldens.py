@@ -31,6 +31,22 @@ def test_oracle_matches_reference_render(oracle, name, model):
     assert st.paths == W * H * SPP
 
 
+def test_oracle_matches_reference_stage5_normals(oracle):
+    """outputs/5_anti_aliasing.png (320x180, 100 spp, normals as colours, no tonemapping): an almost noise-free pin of
+    Camera.get_rays (pinhole, pixel jitter), Sphere.hit / World.hit, the sky and the imwrite orientation + quantisation."""
+    W, H, SPP = 320, 180, 128
+    world, cam = scenes.scene_5_anti_aliasing((W, H))
+    acc, _, st = oracle.render(oracle.scene_from_world(world), cam.to_struct(), W, H, SPP, 32, L.PT_SHADE_V2_NORMALS, seed=3)
+    img = L.to_uint8(acc / SPP).astype(np.float64)
+    gold = np.asarray(Image.open(os.path.join(GOLDEN, "5_anti_aliasing_320x180.png")).convert("RGB"), np.float64)
+    d = img - gold
+    rmse, bias = float(np.sqrt((d**2).mean())), float(d.mean())
+    assert st.segments == st.paths          # no bounce
+    assert rmse < 1.5, rmse                 # only silhouette pixels carry sampling noise (measured 0.6)
+    assert abs(bias) < 0.3, bias
+    assert float(np.sqrt(((img[::-1] - gold) ** 2).mean())) > 20  # a vertically flipped image is far off
+
+
 def test_segments_per_path_matches_survey(oracle):
     """8_refract averages 2.33 ray segments per path."""
     world, cam = scenes.scene_8_refract((160, 90))
