@@ -382,6 +382,98 @@ def reference_visit_order(tree, n_faces) -> np.ndarray:
     return order
 
 
+def lbvh_to_reference_tree(nodes16, global_prims, tri9, max_leave_objects=4, max_depth=24):
+    """Converts the GPU-built LBVH of ONE mesh (Scene.bvh_download(): [n,16] nodes = two child boxes + two child
+    refs, plus the primitives kept out of the Morton grid) into the node arrays of the reference's MeshBVHTree
+    (15_module.py:716-754): nodes in creation order, `data` = leaf number or -1, leaves as CSR ranges of at most
+    `max_leave_objects` faces (more where the depth bound `max_depth` — the reference's stack size — cuts a deeper
+    subtree).  Returns (tree dict, face order): the file stores faces in leaf order.  SURVEY 8f-1: files written here
+    are traversed efficiently by the reference, no host SAH build needed."""
+    tri9 = np.asarray(tri9, np.float32).reshape(-1, 9)
+    n_faces = len(tri9)
+    plo = tri9.reshape(-1, 3, 3).min(1)
+    phi = tri9.reshape(-1, 3, 3).max(1)
+    kids = nodes16[:, 12:14].copy().view(np.int32) if len(nodes16) else np.zeros((0, 2), np.int32)
+
+    def subtree_prims(ref):
+        out, stack = [], [int(ref)]
+        while stack:
+            r = stack.pop()
+            if r < 0:
+                out.append(~r)
+            else:
+                stack.append(int(kids[r, 1]))
+                stack.append(int(kids[r, 0]))
+        return out
+
+    # number of primitives below every LBVH node (children always have larger or smaller indices: explicit post-order)
+    count = np.zeros(len(nodes16), np.int64)
+    if len(nodes16):
+        order, stack = [], [0]
+        while stack:
+            r = stack.pop()
+            order.append(r)
+            for c in kids[r]:
+                if c >= 0:
+                    stack.append(int(c))
+        for r in reversed(order):
+            count[r] = sum(1 if c < 0 else count[c] for c in kids[r])
+
+    left, right, low, high, data, cut, face_order = [], [], [], [], [], [0], []
+
+    def box_of(prims):
+        return plo[prims].min(0), phi[prims].max(0)
+
+    def new_node(lo, hi):
+        left.append(-1); right.append(-1); low.append(np.asarray(lo, np.float32)); high.append(np.asarray(hi, np.float32))
+        data.append(-1)
+        return len(left) - 1
+
+    def make_leaf(idx, prims):
+        data[idx] = len(cut) - 1
+        face_order.extend(prims)
+        cut.append(len(face_order))
+
+    glob = [int(g) for g in global_prims]
+    all_lo, all_hi = box_of(np.arange(n_faces))
+    root = new_node(all_lo, all_hi)
+    work = []  # (reference node, LBVH ref, depth)
+    if len(nodes16) == 0:  # tree-less mesh (<= 8 faces): one leaf
+        make_leaf(root, list(range(n_faces)))
+    elif glob:  # root -> [leaf of the oversized faces, the LBVH]
+        lo, hi = box_of(glob)
+        a = new_node(lo, hi)
+        rest = sorted(set(range(n_faces)) - set(glob))
+        lo, hi = box_of(rest)
+        b = new_node(lo, hi)
+        left[root], right[root] = a, b
+        make_leaf(a, glob)
+        work.append((b, 0, 1))
+    else:
+        work.append((root, 0, 0))
+    qi = 0
+    while qi < len(work):  # breadth first, like the reference's builder
+        idx, ref, depth = work[qi]
+        qi += 1
+        if ref < 0:
+            make_leaf(idx, [~ref])
+            continue
+        if count[ref] <= max_leave_objects or depth >= max_depth:
+            make_leaf(idx, subtree_prims(ref))
+            continue
+        n = nodes16[ref]
+        a = new_node(n[0:3], n[3:6])
+        b = new_node(n[6:9], n[9:12])
+        left[idx], right[idx] = a, b
+        work.append((a, int(kids[ref, 0]), depth + 1))
+        work.append((b, int(kids[ref, 1]), depth + 1))
+    face_order = np.asarray(face_order, np.int64)
+    assert len(face_order) == n_faces and len(np.unique(face_order)) == n_faces
+    tree = {"left": np.asarray(left, np.int32), "right": np.asarray(right, np.int32), "low": np.stack(low), "high": np.stack(high),
+            "data": np.asarray(data, np.int32), "leaf_cut": np.asarray(cut, np.int32), "max_depth": int(max_depth)}
+    return tree, face_order
+
+
 # ---- world -------------------------------------------------------------------------------------------
 class World:
     """15_module.py:782-848."""
@@ -466,7 +558,31 @@ class World:
         self.load_textures()
 
     # -- persistence
-    def save(self, filename):
+    def build_trees(self, ctx=None, max_leave_objects=4, max_depth=24):
+        """Gives every mesh that has no stored tree one in the reference's schema, from an LBVH built on the GPU
+        (replaces the reference's host-Python SAH build, 15_module.py:716-754, minutes -> milliseconds); faces are
+        reordered to leaf order as in the reference's files."""
+        from .render import default_context
+        ctx = ctx or default_context()
+        for m in self.meshes:
+            if m.get("tree") is not None:
+                continue
+            f = m["indices"]
+            tri9 = m["positions"][f[:, [0, 3, 6]]].reshape(-1, 9)
+            sc = _lib.Scene(ctx)
+            sc.set_triangles(tri9)
+            sc.build()
+            nodes, glob = sc.bvh_download()
+            sc.close()
+            tree, order = lbvh_to_reference_tree(nodes, glob, tri9, max_leave_objects, max_depth)
+            m["tree"], m["indices"] = tree, f[order]
+        self._scene = None
+
+    def save(self, filename, build_trees=True, ctx=None):
+        """World.save (15_module.py:815-821).  Meshes without a stored tree get one from the GPU builder first
+        (build_trees=False writes a single-leaf tree instead, valid but brute force for the reference)."""
+        if build_trees and any(m.get("tree") is None for m in self.meshes):
+            self.build_trees(ctx)
         meshes = [{"positions": m["positions"], "normals": m["normals"], "texcoords": m["texture_coords"],
                    "faces": m["indices"], "tree": m["tree"]} for m in self.meshes]
         spheres = None

@@ -156,3 +156,31 @@ def test_legacy_renderer_progressive(ctx):
     assert not np.allclose(f1, f2)
     f3 = lr.render(moved=True)
     assert lr.total_spp == 8 and np.allclose(f3, f1, rtol=2e-3, atol=2e-3, equal_nan=True)
+
+
+def test_gpu_built_trees_are_valid_reference_files(ctx, oracle, tmp_path):
+    """SURVEY 8f-1: a world assembled from raw meshes is saved with trees from the GPU LBVH in the reference's schema;
+    the oracle, walking the stored tree exactly like MeshBVHTree.hit, finds what a loop over all faces finds, and the
+    reloaded world renders the same hits on the GPU."""
+    from learn_path_tracing_b200 import legacy, worldnpy
+    w, cam = synthetic_legacy_world(grid=40)      # 3200-face bumpy grid + ground quad + 2 spheres, no stored trees
+    assert all(m["tree"] is None for m in w.meshes)
+    rays = oracle.generate_rays(cam.to_struct(), 160, 90, 0, 3)
+    ids0, t0 = w.hit(rays, ctx)
+    fn = str(tmp_path / "gpu_tree.world.npy")
+    w.save(fn, ctx=ctx)                              # builds the trees on the GPU
+    assert all(m["tree"] is not None for m in w.meshes)
+    big = w.meshes[0]["tree"]
+    assert len(big["left"]) > 1000 and np.diff(big["leaf_cut"]).max() <= 4 and big["max_depth"] == 24
+    d = worldnpy.load_world(fn)
+    assert len(d["meshes_bvhs"]) == 2
+    w2 = legacy.World()
+    w2.load(fn, load_images=False)
+    w2.set_atlas(*w._atlas)
+    w2.set_environment_image(*w._env) if w._env is not None else None
+    a_id, a_t = oracle.scene_from_legacy_world(w2, use_stored_tree=True).trace(rays)
+    b_id, b_t = oracle.scene_from_legacy_world(w2, use_stored_tree=False).trace(rays)
+    assert np.array_equal(a_t, b_t) and np.array_equal(a_id >= 0, b_id >= 0) and (a_id != b_id).mean() < 0.01
+    ids2, t2 = w2.hit(rays, ctx)                     # faces were reordered to leaf order: compare geometry, not ids
+    assert np.array_equal(t2, t0) and np.array_equal(ids2 >= 0, ids0 >= 0)
+    assert (a_id >= 0).mean() > 0.5

@@ -95,7 +95,7 @@ def test_texture_manager_shelf_packer():
 def test_world_save_load_round_trip(tmp_path):
     w, _ = synthetic_legacy_world()
     fn = str(tmp_path / "s.world.npy")
-    w.save(fn)
+    w.save(fn, build_trees=False)   # no GPU here: single-leaf trees (the GPU-built trees are tested under -m gpu)
     d = worldnpy.load_world(fn)
     assert len(d["meshes_bvhs"]) == 2 and "spheres_bvh" in d
     w2 = legacy.World()
@@ -108,6 +108,60 @@ def test_world_save_load_round_trip(tmp_path):
     w3 = scene_cache.load_cache(c)
     assert np.array_equal(w3._atlas[0], w._atlas[0]) and np.array_equal(w3._env[0], w._env[0])
     assert len(w3.meshes) == 2 and len(w3.spheres) == 2
+
+
+def test_lbvh_to_reference_tree_schema():
+    """LBVH nodes (two child boxes + refs) -> the reference's MeshBVHTree arrays: every face in exactly one leaf,
+    leaves <= 4 faces unless the depth bound cuts, node boxes contain their faces, nodes in creation order."""
+    rng = np.random.default_rng(1)
+    n = 37
+    tri9 = (rng.random((n, 1, 3)) * 4 + rng.random((n, 3, 3)) * 0.3).astype(np.float32).reshape(n, 9)
+    lo, hi = tri9.reshape(n, 3, 3).min(1), tri9.reshape(n, 3, 3).max(1)
+    # a hand-made binary tree over the faces sorted by x: recursive median split, written in the LBVH node layout
+    order = list(np.argsort(lo[:, 0]))
+    nodes = []
+
+    def build(ids):
+        if len(ids) == 1:
+            return ~int(ids[0]), lo[ids[0]], hi[ids[0]]
+        k = len(nodes)
+        nodes.append(None)
+        a, alo, ahi = build(ids[:len(ids) // 2])
+        b, blo, bhi = build(ids[len(ids) // 2:])
+        rec = np.zeros(16, np.float32)
+        rec[0:3], rec[3:6], rec[6:9], rec[9:12] = alo, ahi, blo, bhi
+        rec[12:14] = np.array([a, b], np.int32).view(np.float32)
+        nodes[k] = rec
+        return k, np.minimum(alo, blo), np.maximum(ahi, bhi)
+
+    for glob, depth in (([], 24), ([5, 9], 24), ([], 2)):
+        nodes.clear()
+        build([i for i in order if i not in glob])   # the builder keeps oversized ("global") faces out of the tree
+        nodes16 = np.stack(nodes)
+        tree, forder = legacy.lbvh_to_reference_tree(nodes16, glob, tri9, max_leave_objects=4, max_depth=depth)
+        assert sorted(forder) == list(range(n))
+        L_, R_, D_, cut = tree["left"], tree["right"], tree["data"], tree["leaf_cut"]
+        assert cut[0] == 0 and cut[-1] == n and np.all(np.diff(cut) > 0)
+        leaves = np.flatnonzero(D_ >= 0)
+        assert sorted(D_[leaves]) == list(range(len(cut) - 1))
+        assert np.all((L_[leaves] == -1) & (R_[leaves] == -1))
+        inner = np.flatnonzero(D_ < 0)
+        assert np.all(L_[inner] > inner) and np.all(R_[inner] == L_[inner] + 1)   # creation order, siblings adjacent
+        if depth == 24 and not glob:
+            assert np.diff(cut).max() <= 4
+        # boxes: a leaf's box contains its faces; a child's box lies inside its parent's
+        for k in leaves:
+            f = forder[cut[D_[k]]:cut[D_[k] + 1]]
+            assert np.all(lo[f] >= tree["low"][k] - 1e-6) and np.all(hi[f] <= tree["high"][k] + 1e-6)
+        for k in inner:
+            for c in (L_[k], R_[k]):
+                assert np.all(tree["low"][c] >= tree["low"][k] - 1e-6) and np.all(tree["high"][c] <= tree["high"][k] + 1e-6)
+        # the reference's traversal needs depth <= max_depth (its stack has max_depth + 1 entries)
+        d = np.zeros(len(L_), np.int64)
+        for k in inner:
+            d[L_[k]] = d[R_[k]] = d[k] + 1
+        assert d.max() <= tree["max_depth"]
+        assert legacy.reference_visit_order(tree, n).shape == (n,)
 
 
 def test_legacy_oracle_tree_walk_equals_brute_force(oracle):
