@@ -6,7 +6,7 @@
                                       diffuse maps (full: 2048^2 as recorded; small: 512^2 for tests), ground = documented
                                       constant fallback because granite-gray-white_albedo/_roughness/_normal are absent
     zhongli_{small,full}.npz          Zhongli.world.npy (old format): textures in MTL first-seen order (14_mesh.py:991-999)
-    ganyu_small.npz                   Ganyu.world.npy
+    ganyu_{small,full}.npz            Ganyu.world.npy
     demo.npz                          demo.world.npy: one quad + one textured sphere (unit-test fixture)
 No reference SOURCE is copied: only geometry arrays and images (data) are converted.
 """
@@ -69,6 +69,7 @@ def main():
         ("zhongli_small", lambda: old_format("Zhongli", "Zhongli", 512)),
         ("zhongli_full", lambda: old_format("Zhongli", "Zhongli", 2048)),
         ("ganyu_small", lambda: old_format("Ganyu", "Ganyu", 512)),
+        ("ganyu_full", lambda: old_format("Ganyu", "Ganyu", 2048)),
     ]
     for name, make in jobs:
         path = os.path.join(OUT, name + ".npz")
