@@ -64,6 +64,7 @@ extern "C" {
 #define PT_FLAG_NO_SORT 8       /* keep the batch order (default: batches >= 65536 rays are traced in an
                                    entry-point/direction Morton order; results always land in batch order) */
 #define PT_FLAG_TRACE_SIMPLE 16 /* one ray per thread (k_trace) instead of the persistent while-while warps */
+#define PT_FLAG_NO_QNODES 32    /* walk the 64-byte float nodes even when the tree has the 32-byte quantised copy */
 /* bits 8-13 of the trace flags: lanes that must wait before a warp services them (0 = default 8);
    bits 14-19: finished lanes that trigger result write-back + refill (0 = default 8) */
 

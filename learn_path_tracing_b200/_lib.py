@@ -29,6 +29,7 @@ PT_MODE_FUSED = 2   # k_paths: K segments per launch in registers, compaction at
 PT_MODE_PERSIST = 3  # k_paths_persist: persistent while-while lanes, one launch per render (auto)
 PT_FLAG_NO_SORT = 8        # pt_trace_batch_device: keep batch order
 PT_FLAG_TRACE_SIMPLE = 16  # pt_trace_batch_device: one ray per thread (k_trace)
+PT_FLAG_NO_QNODES = 32     # pt_trace_batch_device: 64-byte float nodes even when the quantised copy exists
 
 
 class PtMaterial(C.Structure):

@@ -7,6 +7,8 @@
 
 #include "pt_internal.h"
 
+#define PT_QNODES_MIN (1 << 18)  // trees from 256 Ki nodes (16 MiB of 64-byte nodes) on get the quantised copy
+
 static thread_local char g_err[1024] = "";
 
 void pt_set_error(const char* fmt, ...) {
@@ -95,11 +97,12 @@ extern "C" int pt_scene_create(PtContext* ctx, PtScene** out) {
 }
 
 static void free_device(PtScene* s) {
-    void* ptrs[] = {s->d_sph_cr, s->d_sph_aux, s->d_sph_mat, s->d_tri_geo, s->d_tri_shade, s->d_nodes, s->d_global};
+    void* ptrs[] = {s->d_sph_cr, s->d_sph_aux, s->d_sph_mat, s->d_tri_geo, s->d_tri_shade, s->d_nodes, s->d_global, s->d_qnodes};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     s->d_sph_cr = s->d_sph_aux = s->d_sph_mat = s->d_tri_geo = s->d_tri_shade = s->d_nodes = nullptr;
     s->d_global = nullptr;
+    s->d_qnodes = nullptr;
     s->built = false;
 }
 
@@ -506,6 +509,16 @@ extern "C" int pt_scene_build(PtScene* s) {
             s->bounds_lo[c] = fminf(lo0[c], lo1[c]);
             s->bounds_hi[c] = fmaxf(hi0[c], hi1[c]);
         }
+    }
+    // big trees also get 32-byte quantised nodes (half the L1 wavefronts and bytes per visit in k_trace_persist)
+    s->view.qnodes = nullptr;
+    if (root != PT_NO_BVH && s->n_nodes >= PT_QNODES_MIN) {
+        float scale[3];
+        for (int c = 0; c < 3; ++c) scale[c] = fmaxf((s->bounds_hi[c] - s->bounds_lo[c]) / 65535.0f, 1e-30f) * (1.0f + 1e-6f);
+        int rcq = pt_quantize_nodes(ctx, s->d_nodes, s->n_nodes, s->bounds_lo, scale, &s->d_qnodes);
+        if (rcq) return rcq;
+        s->view.qnodes = s->d_qnodes;
+        for (int c = 0; c < 3; ++c) { s->view.qlo[c] = s->bounds_lo[c]; s->view.qscale[c] = scale[c]; }
     }
     SceneView& v = s->view;
     v.sph_cr = s->d_sph_cr; v.sph_aux = s->d_sph_aux; v.sph_mat = s->d_sph_mat;

@@ -242,6 +242,56 @@ PT_DEV void node_step(const SceneView& sv, Trav& T, int* stack, TraceCounters& t
     }
 }
 
+// The same step on the 32-byte quantised nodes (one 256-bit load): the child boxes are 12 x u16 in the frame of the
+// root box, and the ray's slab operands are pre-multiplied by that frame (trav_frame_q), so the decode is just the
+// twelve integer -> float conversions (I2F.U16 with half-register selectors; an ALU-only decode via the 2^23 + q
+// float trick measured the same, so the XU pipe is not what limits this kernel).
+PT_DEV void trav_frame_q(const SceneView& sv, float3 o, Trav& T) {  // after trav_begin: t = q * (scale * inv) + (lo - o) * inv
+    T.oi = f3((sv.qlo[0] - o.x) * T.inv.x, (sv.qlo[1] - o.y) * T.inv.y, (sv.qlo[2] - o.z) * T.inv.z);
+    T.inv = f3(sv.qscale[0] * T.inv.x, sv.qscale[1] * T.inv.y, sv.qscale[2] * T.inv.z);
+}
+struct __align__(32) QNode8 {
+    unsigned w[8];
+};
+PT_DEV QNode8 ldg256u(const void* p) {
+    QNode8 r;
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+        : "l"(p));
+    return r;
+}
+PT_DEV float qlo16(unsigned w) { return (float)(unsigned short)w; }
+PT_DEV float qhi16(unsigned w) { return (float)(unsigned short)(w >> 16); }
+
+template <bool COUNT>
+PT_DEV void node_step_q(const SceneView& sv, Trav& T, int* stack, TraceCounters& tc) {
+    if (COUNT) tc.nodes++;
+    const QNode8 N = ldg256u(sv.qnodes + 2 * (size_t)T.cur);
+    // w0 = c0.min x|y, w1 = c0.min z | c0.max x, w2 = c0.max y|z, w3 = c1.min x|y, w4 = c1.min z | c1.max x, w5 = c1.max y|z
+    const float3 inv = T.inv, oi = T.oi;
+    float x0 = fmaf(qlo16(N.w[0]), inv.x, oi.x), x1 = fmaf(qhi16(N.w[1]), inv.x, oi.x);
+    float y0 = fmaf(qhi16(N.w[0]), inv.y, oi.y), y1 = fmaf(qlo16(N.w[2]), inv.y, oi.y);
+    float z0 = fmaf(qlo16(N.w[1]), inv.z, oi.z), z1 = fmaf(qhi16(N.w[2]), inv.z, oi.z);
+    const float t0a = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+    const float t1a = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), T.best));
+    x0 = fmaf(qlo16(N.w[3]), inv.x, oi.x); x1 = fmaf(qhi16(N.w[4]), inv.x, oi.x);
+    y0 = fmaf(qhi16(N.w[3]), inv.y, oi.y); y1 = fmaf(qlo16(N.w[5]), inv.y, oi.y);
+    z0 = fmaf(qlo16(N.w[4]), inv.z, oi.z); z1 = fmaf(qhi16(N.w[5]), inv.z, oi.z);
+    const float t0b = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+    const float t1b = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), T.best));
+    const bool ha = t0a <= t1a, hb = t0b <= t1b;
+    const int ca = (int)N.w[6], cb = (int)N.w[7];
+    if (ha && hb) {
+        const bool a_first = t0a <= t0b;
+        stack[T.sp++] = a_first ? cb : ca;
+        T.cur = a_first ? ca : cb;
+    } else if (ha || hb) {
+        T.cur = ha ? ca : cb;
+    } else {
+        T.cur = stack[--T.sp];
+    }
+}
+
 // Leaf step: tests primitive ~T.cur and pops.
 template <bool COUNT>
 PT_DEV void leaf_step(const SceneView& sv, float3 o, float3 d, float tmin, Trav& T, int* stack, TraceCounters& tc) {

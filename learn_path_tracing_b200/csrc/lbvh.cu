@@ -146,6 +146,33 @@ __global__ void k_refit_emit(long long n, const int2* __restrict__ children, con
     }
 }
 
+// Quantised copy of the nodes for big trees: child boxes as u16 in the root frame, conservative (a min never
+// dequantises above the float min, a max never below the float max, checked with the traversal's own fmaf).
+__device__ __forceinline__ unsigned q_down(float v, float lo, float scale) {
+    int q = (int)floor(((double)v - (double)lo) / (double)scale);
+    q = q < 0 ? 0 : (q > 65535 ? 65535 : q);
+    while (q > 0 && fmaf((float)q, scale, lo) > v) --q;
+    return (unsigned)q;
+}
+__device__ __forceinline__ unsigned q_up(float v, float lo, float scale) {
+    int q = (int)ceil(((double)v - (double)lo) / (double)scale);
+    q = q < 0 ? 0 : (q > 65535 ? 65535 : q);
+    while (q < 65535 && fmaf((float)q, scale, lo) < v) ++q;
+    return (unsigned)q;
+}
+__global__ void k_quantize_nodes(const float4* __restrict__ nodes, long long n, float3 lo, float3 sc, uint4* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = nodes[4 * i], b = nodes[4 * i + 1], c = nodes[4 * i + 2], k = nodes[4 * i + 3];
+    // child 0: min a.x a.y a.z max a.w b.x b.y; child 1: min b.z b.w c.x max c.y c.z c.w
+    const unsigned m0x = q_down(a.x, lo.x, sc.x), m0y = q_down(a.y, lo.y, sc.y), m0z = q_down(a.z, lo.z, sc.z);
+    const unsigned M0x = q_up(a.w, lo.x, sc.x), M0y = q_up(b.x, lo.y, sc.y), M0z = q_up(b.y, lo.z, sc.z);
+    const unsigned m1x = q_down(b.z, lo.x, sc.x), m1y = q_down(b.w, lo.y, sc.y), m1z = q_down(c.x, lo.z, sc.z);
+    const unsigned M1x = q_up(c.y, lo.x, sc.x), M1y = q_up(c.z, lo.y, sc.y), M1z = q_up(c.w, lo.z, sc.z);
+    out[2 * i] = make_uint4(m0x | m0y << 16, m0z | M0x << 16, M0y | M0z << 16, m1x | m1y << 16);
+    out[2 * i + 1] = make_uint4(m1z | M1x << 16, M1y | M1z << 16, __float_as_uint(k.x), __float_as_uint(k.y));
+}
+
 struct Scratch {
     std::vector<void*> ptrs;
     ~Scratch() { for (void* p : ptrs) cudaFree(p); }
@@ -209,5 +236,22 @@ int pt_lbvh_build(PtContext* ctx, const float4* d_prim_aabb, const int* d_local_
     *d_nodes_out = nodes;
     *n_nodes_out = n - 1;
     *root_out = 0;
+    return PT_OK;
+}
+
+int pt_quantize_nodes(PtContext* ctx, const float4* d_nodes, int64_t n_nodes, const float lo[3], const float scale[3],
+                      uint4** d_qnodes_out) {
+    uint4* q = nullptr;
+    PT_CUDA(cudaMalloc(&q, (size_t)n_nodes * 2 * sizeof(uint4)));
+    k_quantize_nodes<<<(unsigned)((n_nodes + 255) / 256), 256, 0, ctx->stream>>>(
+        d_nodes, n_nodes, make_float3(lo[0], lo[1], lo[2]), make_float3(scale[0], scale[1], scale[2]), q);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        cudaFree(q);
+        pt_set_error("pt_quantize_nodes: %s", cudaGetErrorString(e));
+        return PT_ERR_CUDA;
+    }
+    *d_qnodes_out = q;
     return PT_OK;
 }

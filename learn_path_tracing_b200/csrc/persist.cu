@@ -173,7 +173,7 @@ k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* _
 // Fixed ray batch (pt_trace_batch*, BASELINE configs[4]): persistent warps, rays drawn dynamically from
 // one counter in the order given by `order` (a sort by entry point and direction, see k_ray_keys; NULL =
 // batch order).  Result i is written to hits[i] of the ORIGINAL batch order.
-template <bool COUNT>
+template <bool COUNT, bool QNODES>
 __global__ void __launch_bounds__(PT_BLOCK, 4)
 k_trace_persist(const SceneView sv, const float4* __restrict__ rays, const unsigned* __restrict__ order,
                 float4* __restrict__ hits, long long n, unsigned long long* __restrict__ counters, int serve_min,
@@ -196,9 +196,13 @@ k_trace_persist(const SceneView sv, const float4* __restrict__ rays, const unsig
         const int n_inner = __popc(__ballot_sync(0xffffffffu, inner));
         if (n_inner > walk_min) {
             if (inner) {
-                node_step<COUNT>(sv, T, stack, tc);
+                if (QNODES) node_step_q<COUNT>(sv, T, stack, tc);
+                else node_step<COUNT>(sv, T, stack, tc);
                 // a second step on the same vote (the vote costs about a quarter of a step)
-                if (n_inner > walk_min + 4 && PT_IS_INNER(T.cur)) node_step<COUNT>(sv, T, stack, tc);
+                if (n_inner > walk_min + 4 && PT_IS_INNER(T.cur)) {
+                    if (QNODES) node_step_q<COUNT>(sv, T, stack, tc);
+                    else node_step<COUNT>(sv, T, stack, tc);
+                }
             }
             continue;
         }
@@ -227,6 +231,7 @@ k_trace_persist(const SceneView sv, const float4* __restrict__ rays, const unsig
                         const float4 ro = __ldg(&rays[2 * ray]), rd = __ldg(&rays[2 * ray + 1]);
                         o = f3(ro); d = f3(rd); tmin = ro.w;
                         trav_begin<COUNT>(sv, o, d, tmin, rd.w, T, stack, tc);
+                        if (QNODES) trav_frame_q(sv, o, T);
                         st = ST_TRAV;
                     } else {
                         st = ST_DEAD;
@@ -311,7 +316,7 @@ static int resident_blocks(PtContext* ctx, K kernel, int* out) {
 }
 
 int pt_trace_persist(PtContext* ctx, const PtScene* s, const float4* rays, long long n, float4* hits, bool count,
-                     bool sort, int serve_min, int fetch_min, cudaEvent_t ev_sorted) {
+                     bool sort, bool use_qnodes, int serve_min, int fetch_min, cudaEvent_t ev_sorted) {
     cudaStream_t st = ctx->stream;
     const unsigned* order = nullptr;
     if (sort && n > 1) {
@@ -335,13 +340,19 @@ int pt_trace_persist(PtContext* ctx, const PtScene* s, const float4* rays, long 
     }
     if (ev_sorted) PT_CUDA(cudaEventRecord(ev_sorted, st));
     int blocks = 0, rcb;
-    if (count) rcb = resident_blocks(ctx, k_trace_persist<true>, &blocks);
-    else rcb = resident_blocks(ctx, k_trace_persist<false>, &blocks);
+    const bool q = s->view.qnodes != nullptr && use_qnodes;
+    if (count) rcb = q ? resident_blocks(ctx, k_trace_persist<true, true>, &blocks) : resident_blocks(ctx, k_trace_persist<true, false>, &blocks);
+    else rcb = q ? resident_blocks(ctx, k_trace_persist<false, true>, &blocks) : resident_blocks(ctx, k_trace_persist<false, false>, &blocks);
     if (rcb) return rcb;
     const long long need = (n + PT_BLOCK - 1) / PT_BLOCK;
     if (blocks > need) blocks = (int)need;
-    if (count) k_trace_persist<true><<<blocks, PT_BLOCK, 0, st>>>(s->view, rays, order, hits, n, ctx->counters, serve_min, fetch_min);
-    else k_trace_persist<false><<<blocks, PT_BLOCK, 0, st>>>(s->view, rays, order, hits, n, ctx->counters, serve_min, fetch_min);
+    if (count) {
+        if (q) k_trace_persist<true, true><<<blocks, PT_BLOCK, 0, st>>>(s->view, rays, order, hits, n, ctx->counters, serve_min, fetch_min);
+        else k_trace_persist<true, false><<<blocks, PT_BLOCK, 0, st>>>(s->view, rays, order, hits, n, ctx->counters, serve_min, fetch_min);
+    } else {
+        if (q) k_trace_persist<false, true><<<blocks, PT_BLOCK, 0, st>>>(s->view, rays, order, hits, n, ctx->counters, serve_min, fetch_min);
+        else k_trace_persist<false, false><<<blocks, PT_BLOCK, 0, st>>>(s->view, rays, order, hits, n, ctx->counters, serve_min, fetch_min);
+    }
     PT_CUDA(cudaGetLastError());
     return PT_OK;
 }

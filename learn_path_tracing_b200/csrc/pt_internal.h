@@ -35,6 +35,10 @@ struct SceneView {
     const float4* tri_geo;
     const float4* tri_shade;
     const float4* nodes;
+    // 32-byte nodes for big trees (trace kernel): the same two child boxes as 12 x u16 in the frame of the root box
+    // (mins rounded down, maxes up) + the two child refs; NULL when the tree is small
+    const uint4* qnodes;
+    float qlo[3], qscale[3];  // coordinate = qlo + q * qscale
     const int* global_prims;
     const uint2* atlas;
     const int4* tex_areas;
@@ -104,6 +108,7 @@ struct PtScene {
     // device
     float4 *d_sph_cr = nullptr, *d_sph_aux = nullptr, *d_sph_mat = nullptr;
     float4 *d_tri_geo = nullptr, *d_tri_shade = nullptr, *d_nodes = nullptr;
+    uint4* d_qnodes = nullptr;
     int* d_global = nullptr;
     uint2* d_atlas = nullptr;
     int4* d_tex_areas = nullptr;
@@ -143,11 +148,14 @@ int pt_lbvh_build(PtContext* ctx, const float4* d_prim_aabb, const int* d_local_
 
 // wavefront.cu
 int pt_ensure_pool(PtContext* ctx, size_t capacity);
+// lbvh.cu — 64-byte nodes -> 32-byte quantised nodes in the frame [lo, lo + 65535 * scale]
+int pt_quantize_nodes(PtContext* ctx, const float4* d_nodes, int64_t n_nodes, const float lo[3], const float scale[3],
+                      uint4** d_qnodes_out);
 // persist.cu — persistent while-while kernels (PT_MODE_PERSIST)
 struct RenderConsts;
 int pt_render_persist(PtContext* ctx, const PtScene* s, const RenderConsts& rc, bool legacy, bool count, float4* accum,
                       float4* accum_sq, int shade_min, int serve_min);
 int pt_trace_persist(PtContext* ctx, const PtScene* s, const float4* rays, long long n, float4* hits, bool count,
-                     bool sort, int serve_min, int fetch_min, cudaEvent_t ev_sorted);
+                     bool sort, bool use_qnodes, int serve_min, int fetch_min, cudaEvent_t ev_sorted);
 // post.cu
 int pt_ensure_scratch(PtContext* ctx, size_t bytes);
