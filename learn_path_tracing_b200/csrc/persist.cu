@@ -173,8 +173,10 @@ k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* _
 // Fixed ray batch (pt_trace_batch*, BASELINE configs[4]): persistent warps, rays drawn dynamically from
 // one counter in the order given by `order` (a sort by entry point and direction, see k_ray_keys; NULL =
 // batch order).  Result i is written to hits[i] of the ORIGINAL batch order.
+// 6 blocks of 256 threads per SM (40 registers, a few spilled words): ncu shows this kernel latency-bound (long
+// scoreboard 8.7 warps per issue at 4 blocks); measured 1.34 / 1.54 / 1.62 Grays/s at 4 / 5 / 6 blocks, 0.93 at 7+
 template <bool COUNT, bool QNODES>
-__global__ void __launch_bounds__(PT_BLOCK, 4)
+__global__ void __launch_bounds__(PT_BLOCK, 6)
 k_trace_persist(const SceneView sv, const float4* __restrict__ rays, const unsigned* __restrict__ order,
                 float4* __restrict__ hits, long long n, unsigned long long* __restrict__ counters, int serve_min,
                 int fetch_min) {
