@@ -155,7 +155,7 @@ struct Texel {
 };
 PT_DEV void texel_accum(const SceneView& sv, int x, int y, float wgt, bool want_normal, Texel& o) {
     if (x < 0 || y < 0 || x >= sv.tex_W || y >= sv.tex_H) return;  // outside the field: zero
-    const uint2 q = __ldg(&sv.atlas[(size_t)x * sv.tex_H + y]);
+    const uint2 q = __ldcg(&sv.atlas[(size_t)x * sv.tex_H + y]);  // L2 only: the atlas must not evict BVH nodes from L1
     const float* la = sv.lut;
     const float* ls = sv.lut + 256;
     o.albedo.x = fmaf(wgt, __ldg(la + (q.x & 255u)), o.albedo.x);
@@ -187,7 +187,7 @@ PT_DEV Texel sample_texture(const SceneView& sv, int id, float u, float v, bool 
 }
 PT_DEV float3 env_fetch(const SceneView& sv, int x, int y) {
     if (x < 0 || y < 0 || x >= sv.env_W || y >= sv.env_H) return f3(0, 0, 0);
-    return f3(__ldg(&sv.env[(size_t)x * sv.env_H + y]));
+    return f3(__ldcg(&sv.env[(size_t)x * sv.env_H + y]));
 }
 PT_DEV float3 environment_color(const SceneView& sv, float3 d) {  // 15_module.py:970-977
     if (!sv.has_env) return sky_color(d);
@@ -234,7 +234,7 @@ PT_DEV void scatter_legacy(const SceneView& sv, PathState& p, const Hit& h, floa
         transparency = __float_as_int(aux.y);
     } else {  // triangle_hit, 15_module.py:929-950
         const float4* s = sv.tri_shade + 4 * (size_t)(h.prim - sv.n_sph);
-        const float4 s0 = __ldg(s), s1 = __ldg(s + 1), s2 = __ldg(s + 2), s3 = __ldg(s + 3);
+        const float4 s0 = __ldcg(s), s1 = __ldcg(s + 1), s2 = __ldcg(s + 2), s3 = __ldcg(s + 3);
         const float w1 = 1.0f - h.u - h.v, w2 = h.u, w3 = h.v;
         normal = normalize(w1 * f3(s0) + w2 * f3(s1) + w3 * f3(s2));
         const float uu = w1 * s0.w + w2 * s2.w + w3 * s3.y;
