@@ -104,7 +104,8 @@ typedef struct PtRenderParams {
     int32_t pool_capacity;  /* path-pool slots; 0 = library default                                 */
     int32_t flags;          /* PT_FLAG_*                                                            */
     int32_t reserved[6];    /* [0] wavefront mode: 0 auto (= 3), 1 split (k_extend +
-                                   k_shade per bounce), 2 fused K-step (k_paths), 3 persistent while-while (k_paths_persist)
+                                   k_shade per bounce), 2 fused K-step (k_paths), 3 persistent ballot-scheduled (k_paths_persist),
+                                   4 experimental: persistent + block-local shading queues (k_paths_queue, slower)
                                [1] fused mode: ray segments per path slot per launch (0 = default 32)
                                [2] persistent mode: finished lanes that trigger shading + refill (0 = default 12)
                                [3] persistent mode: waiting lanes that trigger a service (leaf tests) (0 = default 8)  */

@@ -20,6 +20,7 @@
 #define PT_MODE_SPLIT 1
 #define PT_MODE_FUSED 2
 #define PT_MODE_PERSIST 3
+#define PT_MODE_QUEUE 4
 
 struct RenderConsts {
     CameraDev cam;

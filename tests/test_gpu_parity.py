@@ -152,7 +152,8 @@ def test_fused_and_split_wavefronts_trace_the_same_paths(ctx):
     ref = None
     for mode, cap, k, tm in [(L.PT_MODE_SPLIT, 0, 0, 0), (L.PT_MODE_FUSED, 0, 0, 0), (L.PT_MODE_FUSED, 1024, 3, 0),
                              (L.PT_MODE_FUSED, 7000, 1, 0), (L.PT_MODE_SPLIT, 2048, 0, 0), (L.PT_MODE_PERSIST, 0, 0, 0),
-                             (L.PT_MODE_PERSIST, 0, 0, 32), (L.PT_MODE_PERSIST, 0, 0, 1), (L.PT_MODE_AUTO, 0, 0, 0)]:
+                             (L.PT_MODE_PERSIST, 0, 0, 32), (L.PT_MODE_PERSIST, 0, 0, 1), (L.PT_MODE_AUTO, 0, 0, 0),
+                             (L.PT_MODE_QUEUE, 0, 0, 0), (L.PT_MODE_QUEUE, 0, 0, 1), (L.PT_MODE_QUEUE, 0, 0, 32)]:
         r = L.Renderer(W, H, ctx)
         st = r.render(sc, cam.to_struct(), 24, 32, seed=5, mode=mode, pool_capacity=cap, segments_per_launch=k,
                       serve_min=tm)
