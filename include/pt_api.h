@@ -107,7 +107,7 @@ typedef struct PtRenderParams {
                                    k_shade per bounce), 2 fused K-step (k_paths), 3 persistent ballot-scheduled (k_paths_persist),
                                    4 experimental: persistent + block-local shading queues (k_paths_queue, slower)
                                [1] fused mode: ray segments per path slot per launch (0 = default 32)
-                               [2] persistent mode: finished lanes that trigger shading + refill (0 = default 12)
+                               [2] persistent mode: finished lanes that trigger shading + refill (0 = default 22)
                                [3] persistent mode: waiting lanes that trigger a service (leaf tests) (0 = default 8)  */
 } PtRenderParams; /* 64 bytes */
 
