@@ -292,6 +292,11 @@ PT_DEV void camera_ray(const CameraDev& c, int i, int j, float4 u, float3* o, fl
     const float fx = ((float)i + u.x) * c.inv_w - 0.5f;
     const float fy = ((float)j + u.y) * c.inv_h - 0.5f;
     const float3 target = c.focal * (c.front + (fx * c.view_w) * c.right + (fy * c.view_h) * c.up);
+    if (c.aperture == 0.0f) {  // pinhole (warp-uniform): the lens sample is multiplied by zero in the reference, skip it
+        *o = c.pos;
+        *d = normalize(target);
+        return;
+    }
     const float r = sqrtf(u.z);  // sample_in_disk, camera.py:29-35
     float s, cs;
     sincos_2pi(u.w, &s, &cs);
