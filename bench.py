@@ -30,6 +30,7 @@ WORKLOADS = {
     # name: (scene, W, H, spp, depth)
     "8_refract_1080p": ("8_refract", 1920, 1080, 256, 50),      # BASELINE configs[1]: the headline workload
     "10_final_720p": ("10_final", 1280, 720, 256, 32),          # configs[0] scene at reduced spp (8192 in the script)
+    "10_final_720p_8192": ("10_final", 1280, 720, 8192, 32),    # configs[0] exactly: the script's default resolution/spp/depth
     "9_dof_720p": ("9_dof", 1280, 720, 256, 32),
     # legacy mesh scenes (need scenes_cache/*.npz from tools/prepare_assets.py): configs[2] and configs[3]
     "yoimiya_1080p": ("cache:yoimiya_ground_full", 1920, 1080, 512, 32),
@@ -330,9 +331,10 @@ def run_ours(args):
                          "traffic_source": traffic["source"] if traffic else None, "peak_kind": peak_kind,
                          "launches": n_k, "avg_launch_ms": ms_k / max(n_k, 1),
                          "algorithmic_bytes_per_launch": bytes_k / max(n_k, 1),
-                         "algorithmic_bytes": "160 B/segment + 24 B/path for the whole wavefront step (k_paths); split mode: k_shade 112 B/segment + 24 B/path, k_extend 48 B/segment (SURVEY 8d)",
+                         "algorithmic_bytes": "160 B/segment + 24 B/path for the whole wavefront step (k_paths_persist, k_paths); split mode: k_shade 112 B/segment + 24 B/path, k_extend 48 B/segment (SURVEY 8d)",
                          "whole_render_160B_per_segment": {"achieved": whole, "frac": whole / peak},
-                         "kernel_ms": {"k_extend": ms_ext / K, "k_shade": ms_sh / K, "step": t_local / K}},
+                         "kernel_ms": ({kname: ms_sh / K, "step": t_local / K} if n_ext == 0 else
+                                       {"k_extend": ms_ext / K, "k_shade": ms_sh / K, "step": t_local / K})},
             "fp32_peak_tflops_measured": fp32_peak,
             "roofline_fp32": {"bound": "fp32", "achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                               "frac": (fp32_achieved / fp32_peak) if fp32_peak else None,
