@@ -166,6 +166,29 @@ def test_fused_and_split_wavefronts_trace_the_same_paths(ctx):
         assert abs(m.mean() / ref.mean() - 1) < 1e-4
 
 
+@pytest.mark.parametrize("size,spp", [((101, 53), 19), ((7, 3), 40), ((1, 1), 64), ((33, 130), 1)])
+def test_odd_image_sizes_and_sample_counts_agree_across_kernels(ctx, size, spp):
+    """Image sizes that are no multiple of the 8x4 tile, sample counts that are no multiple of the 16-sample work
+    unit, images smaller than a warp: every kernel form renders the same paths (and exactly W*H*spp of them)."""
+    W, H = size
+    world, cam = scenes.scene_10_final((W, H))
+    sc = world.device_scene(ctx)
+    ref = None
+    for mode in (L.PT_MODE_SPLIT, L.PT_MODE_FUSED, L.PT_MODE_PERSIST, L.PT_MODE_QUEUE):
+        r = L.Renderer(W, H, ctx)
+        st = r.render(sc, cam.to_struct(), spp, 32, seed=11, mode=mode)
+        acc = r.accum.cpu().numpy()
+        assert st.paths == W * H * spp
+        if ref is None:
+            ref, seg = acc, int(st.segments)
+        assert int(st.segments) == seg or abs(int(st.segments) - seg) <= 1e-3 * seg
+        assert np.array_equal(acc[:, 3], ref[:, 3])                    # contributing paths per pixel: exact
+        assert np.allclose(acc[:, :3], ref[:, :3], rtol=2e-3, atol=2e-4 * spp)
+    empty = L.Renderer(W, H, ctx)
+    st0 = empty.render(sc, cam.to_struct(), 0, 32, seed=11)            # zero samples: nothing happens
+    assert st0.paths == 0 and st0.segments == 0 and float(empty.accum.abs().sum()) == 0.0
+
+
 def test_progressive_and_sample_split_equal_single_render(ctx):
     """spp_offset makes renders splittable (multi-GPU) and continuable (legacy render(moved=False)):
     the union of sample ranges is the same set of paths as one render."""
