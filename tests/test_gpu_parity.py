@@ -256,8 +256,14 @@ def test_trace_kernels_agree_bit_for_bit(ctx, oracle):
     sc.build()
     rays = torch.empty((2 * n_rays, 4), dtype=torch.float32, device="cuda")
     ctx.random_rays_device(rays.data_ptr(), n_rays, 999)
+    # ray intervals: a third of the rays get a finite tmax (some shorter than their first hit), a third a large tmin
+    g = torch.Generator(device="cuda").manual_seed(5)
+    u = torch.rand(n_rays, generator=g, device="cuda")
+    rays[1::2, 3] = torch.where(u < 0.33, 0.3 + 2.0 * torch.rand(n_rays, generator=g, device="cuda"), rays[1::2, 3])
+    rays[0::2, 3] = torch.where(u > 0.66, 0.5 + torch.rand(n_rays, generator=g, device="cuda"), rays[0::2, 3])
     ref = None
-    for flags in (L.PT_FLAG_TRACE_SIMPLE, 0, L.PT_FLAG_NO_SORT, 1 << 8 | 1 << 14, 32 << 8 | 32 << 14, L.PT_FLAG_COUNTERS):
+    for flags in (L.PT_FLAG_TRACE_SIMPLE, 0, L.PT_FLAG_NO_SORT, L.PT_FLAG_NO_QNODES, 1 << 8 | 1 << 14, 32 << 8 | 32 << 14,
+                  L.PT_FLAG_COUNTERS):
         hits = torch.full((n_rays, 4), 7.0, dtype=torch.float32, device="cuda")
         st = ctx.trace_batch_device(sc, rays.data_ptr(), n_rays, hits.data_ptr(), flags)
         torch.cuda.synchronize()
@@ -274,7 +280,12 @@ def test_trace_kernels_agree_bit_for_bit(ctx, oracle):
     r_h = rays[:2 * 20000].cpu().numpy().reshape(-1, 8)
     oid, ot, _ = oracle.trace_bvh2(nodes, tris, r_h)
     gid = ref[:20000, 1]
-    assert (gid == oid).mean() > 0.999
+    plain = (r_h[:, 3] == np.float32(1e-4)) & np.isinf(r_h[:, 7])   # the oracle's tree walk knows only the default interval
+    assert plain.sum() > 5000 and (gid[plain] == oid[plain]).mean() > 0.999
+    t_g = ref[:20000, 0].view(np.float32)
+    hit = gid >= 0
+    assert np.all(t_g[hit] >= r_h[hit, 3]) and np.all(t_g[hit] <= r_h[hit, 7])   # every hit lies inside its ray's interval
+    assert (~hit).mean() > 0.1 and hit.mean() > 0.1
 
 
 def test_device_triangle_generator_matches_oracle(ctx, oracle):
