@@ -28,6 +28,7 @@ PT_MODE_SPLIT = 1   # classic wavefront: k_extend + k_shade per bounce, pool ref
 PT_MODE_FUSED = 2   # k_paths: K segments per launch in registers, compaction at write-back (the HBM path-pool wavefront)
 PT_MODE_PERSIST = 3  # k_paths_persist: persistent while-while lanes, one launch per render (auto)
 PT_MODE_QUEUE = 4    # k_paths_queue: persistent lanes + block-local shading queues in shared memory
+PT_MODE_DUAL = 5     # k_paths_dual: persistent lanes with a lane-private parking place (two paths per lane)
 PT_FLAG_NO_SORT = 8        # pt_trace_batch_device: keep batch order
 PT_FLAG_TRACE_SIMPLE = 16  # pt_trace_batch_device: one ray per thread (k_trace)
 PT_FLAG_NO_QNODES = 32     # pt_trace_batch_device: 64-byte float nodes even when the quantised copy exists

@@ -157,6 +157,9 @@ int pt_render_persist(PtContext* ctx, const PtScene* s, const RenderConsts& rc, 
                       float4* accum_sq, int shade_min, int serve_min);
 int pt_trace_persist(PtContext* ctx, const PtScene* s, const float4* rays, long long n, float4* hits, bool count,
                      bool sort, bool use_qnodes, int serve_min, int fetch_min, cudaEvent_t ev_sorted);
+// dual.cu — persistent kernel with a lane-private parking place per lane (PT_MODE_DUAL)
+int pt_render_dual(PtContext* ctx, const PtScene* s, const RenderConsts& rc, bool legacy, bool count, float4* accum,
+                   float4* accum_sq, int shade_min, int serve_min, int blocks_per_sm);
 // queue.cu — persistent kernel with block-local shading queues (PT_MODE_QUEUE)
 int pt_render_queue(PtContext* ctx, const PtScene* s, const RenderConsts& rc, bool legacy, bool count, float4* accum,
                     float4* accum_sq, int serve_min);

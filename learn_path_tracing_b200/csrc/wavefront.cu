@@ -444,15 +444,15 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
     PT_REQUIRE(!legacy || s->view.n_sph == 0 || s->view.legacy_spheres, "legacy shading needs legacy (textured) spheres");
     const bool want_sq = (p->flags & PT_FLAG_ACCUM_SQ) != 0;
     PT_REQUIRE(!want_sq || accum_sq_dev, "PT_FLAG_ACCUM_SQ needs accum_sq");
-    PT_REQUIRE(p->reserved[0] >= 0 && p->reserved[0] <= 4, "reserved[0] (wavefront mode) must be 0 ... 4");
+    PT_REQUIRE(p->reserved[0] >= 0 && p->reserved[0] <= 5, "reserved[0] (wavefront mode) must be 0 ... 5");
     PT_REQUIRE(p->reserved[1] >= 0 && p->reserved[1] <= 4096, "reserved[1] (segments per launch) out of range");
     PT_REQUIRE(p->reserved[2] >= 0 && p->reserved[2] <= 32 && p->reserved[3] >= 0 && p->reserved[3] <= 32,
                "reserved[2]/[3] (persistent-mode lane thresholds) must be in [0,32]");
     // auto: the persistent ballot-scheduled kernel (measured faster than the K-step fused wavefront on every
     // workload, tree-less scenes included: 16.3 vs 15.3 Gpaths/s on 8_refract 1080p)
     const int mode = p->reserved[0] != PT_MODE_AUTO ? p->reserved[0] : PT_MODE_PERSIST;
-    PT_REQUIRE(p->shading_model != PT_SHADE_V2_NORMALS || mode == PT_MODE_PERSIST || mode == PT_MODE_QUEUE,
-               "PT_SHADE_V2_NORMALS needs a persistent kernel (mode 0, 3 or 4)");
+    PT_REQUIRE(p->shading_model != PT_SHADE_V2_NORMALS || mode >= PT_MODE_PERSIST,
+               "PT_SHADE_V2_NORMALS needs a persistent kernel (mode 0, 3, 4 or 5)");
     PT_CUDA(cudaSetDevice(ctx->device));
 
     const unsigned long long total = (unsigned long long)p->width * p->height * (unsigned long long)p->spp;
@@ -460,7 +460,7 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
     size_t cap = p->pool_capacity > 0 ? (size_t)p->pool_capacity : def_cap;
     if (cap > total) cap = (size_t)total;
     cap = (cap + PT_BLOCK - 1) / PT_BLOCK * PT_BLOCK;
-    if (cap < PT_BLOCK || mode == PT_MODE_PERSIST || mode == PT_MODE_QUEUE) cap = PT_BLOCK;  // the persistent kernel keeps no pool in HBM
+    if (cap < PT_BLOCK || mode >= PT_MODE_PERSIST) cap = PT_BLOCK;  // the persistent kernel keeps no pool in HBM
     int rc_pool = pt_ensure_pool(ctx, cap);
     if (rc_pool) return rc_pool;
 
@@ -491,6 +491,15 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
         const int serve_min = p->reserved[3] > 0 ? p->reserved[3] : 24;
         if (timing) cudaEventRecord(get_event(ctx, ev_idx++), st);
         rcode = pt_render_queue(ctx, s, rc, legacy, count, (float4*)accum_dev, (float4*)accum_sq_dev, serve_min);
+        if (timing) cudaEventRecord(get_event(ctx, ev_idx++), st);
+        iterations = 1; launches = 1;
+    } else if (mode == PT_MODE_DUAL) {
+        // dual.cu: phases (miss / hit / regen) fire once shade_min lanes want exactly them
+        const int shade_min = p->reserved[2] > 0 ? p->reserved[2] : 20;
+        const int serve_min = p->reserved[3] > 0 ? p->reserved[3] : 8;
+        if (timing) cudaEventRecord(get_event(ctx, ev_idx++), st);
+        rcode = pt_render_dual(ctx, s, rc, legacy, count, (float4*)accum_dev, (float4*)accum_sq_dev, shade_min, serve_min,
+                               p->reserved[1] == 3 ? 3 : 4);
         if (timing) cudaEventRecord(get_event(ctx, ev_idx++), st);
         iterations = 1; launches = 1;
     } else if (mode == PT_MODE_PERSIST) {

@@ -21,6 +21,7 @@
 #define PT_MODE_FUSED 2
 #define PT_MODE_PERSIST 3
 #define PT_MODE_QUEUE 4
+#define PT_MODE_DUAL 5
 
 struct RenderConsts {
     CameraDev cam;

@@ -98,7 +98,7 @@ def test_trace_batch_edge_cases(ctx, oracle):
 
 
 # ---- images: 3 sigma of the Monte Carlo standard error ------------------------------------------
-@pytest.mark.parametrize("mode", [L.PT_MODE_FUSED, L.PT_MODE_SPLIT, L.PT_MODE_PERSIST])
+@pytest.mark.parametrize("mode", [L.PT_MODE_FUSED, L.PT_MODE_SPLIT, L.PT_MODE_PERSIST, L.PT_MODE_DUAL])
 @pytest.mark.parametrize("name,model,depth", [("6_diffuse", L.PT_SHADE_V2_DIFFUSE, 32), ("7_reflect", L.PT_SHADE_V2, 32),
                                               ("8_refract", L.PT_SHADE_V2, 50), ("9_dof", L.PT_SHADE_V2, 32),
                                               ("10_final", L.PT_SHADE_V2, 32)])
@@ -153,7 +153,8 @@ def test_fused_and_split_wavefronts_trace_the_same_paths(ctx):
     for mode, cap, k, tm in [(L.PT_MODE_SPLIT, 0, 0, 0), (L.PT_MODE_FUSED, 0, 0, 0), (L.PT_MODE_FUSED, 1024, 3, 0),
                              (L.PT_MODE_FUSED, 7000, 1, 0), (L.PT_MODE_SPLIT, 2048, 0, 0), (L.PT_MODE_PERSIST, 0, 0, 0),
                              (L.PT_MODE_PERSIST, 0, 0, 32), (L.PT_MODE_PERSIST, 0, 0, 1), (L.PT_MODE_AUTO, 0, 0, 0),
-                             (L.PT_MODE_QUEUE, 0, 0, 0), (L.PT_MODE_QUEUE, 0, 0, 1), (L.PT_MODE_QUEUE, 0, 0, 32)]:
+                             (L.PT_MODE_QUEUE, 0, 0, 0), (L.PT_MODE_QUEUE, 0, 0, 1), (L.PT_MODE_QUEUE, 0, 0, 32),
+                             (L.PT_MODE_DUAL, 0, 0, 0), (L.PT_MODE_DUAL, 0, 3, 0), (L.PT_MODE_DUAL, 0, 0, 1), (L.PT_MODE_DUAL, 0, 3, 32)]:
         r = L.Renderer(W, H, ctx)
         st = r.render(sc, cam.to_struct(), 24, 32, seed=5, mode=mode, pool_capacity=cap, segments_per_launch=k,
                       serve_min=tm)
@@ -174,7 +175,7 @@ def test_odd_image_sizes_and_sample_counts_agree_across_kernels(ctx, size, spp):
     world, cam = scenes.scene_10_final((W, H))
     sc = world.device_scene(ctx)
     ref = None
-    for mode in (L.PT_MODE_SPLIT, L.PT_MODE_FUSED, L.PT_MODE_PERSIST, L.PT_MODE_QUEUE):
+    for mode in (L.PT_MODE_SPLIT, L.PT_MODE_FUSED, L.PT_MODE_PERSIST, L.PT_MODE_QUEUE, L.PT_MODE_DUAL):
         r = L.Renderer(W, H, ctx)
         st = r.render(sc, cam.to_struct(), spp, 32, seed=11, mode=mode)
         acc = r.accum.cpu().numpy()
