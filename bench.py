@@ -445,7 +445,7 @@ def run_intersect(args):
                        "lbvh_build_s": build_s},
             "hit_fraction": float((ids_h >= 0).mean()), "ids_equal_to_oracle": agree,
             "e2e": {"value": n_e / min(te) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(n_e * 32),
-                    "d2h_bytes_per_step": int(n_e * 16)},
+                    "d2h_bytes_per_step": int(n_e * 8)},   # ids (i32) + t (f32); records are unpacked on the device
             "gpu_launches": K, "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic["dram_bytes_per_launch"] if traffic else None,

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200pt.so")
+# PT_LIB_PATH: a variant build of the SAME library (tools/build_variants.sh: A/B experiments); never a fallback
+LIB_PATH = os.environ.get("PT_LIB_PATH") or os.path.join(_HERE, "libb200pt.so")
 
 PT_SHADE_V2 = 0
 PT_SHADE_V2_DIFFUSE = 1

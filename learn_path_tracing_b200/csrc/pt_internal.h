@@ -87,6 +87,10 @@ struct PtContext {
     void *stage_rays_h[2] = {nullptr, nullptr}, *stage_hits_h[2] = {nullptr, nullptr};
     void *stage_rays_d[2] = {nullptr, nullptr}, *stage_hits_d[2] = {nullptr, nullptr};
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    // large host -> device uploads (texture atlas): two pinned chunks filled by a few host threads while the copy
+    // engine drains the other one
+    void* up_h[2] = {nullptr, nullptr};
+    cudaEvent_t up_ev[2] = {nullptr, nullptr};
 };
 
 struct HostMesh {

@@ -576,6 +576,7 @@ class World:
             sc.close()
             tree, order = lbvh_to_reference_tree(nodes, glob, tri9, max_leave_objects, max_depth)
             m["tree"], m["indices"] = tree, f[order]
+            m["_visit_order"] = None
         self._scene = None
 
     def save(self, filename, build_trees=True, ctx=None):
@@ -638,7 +639,9 @@ class World:
             for m in self.meshes:
                 # device primitive order = the reference traversal's visitation order, so that "lowest id wins an
                 # exact tie" (extend.cuh) picks the face the reference would have kept
-                order = reference_visit_order(m.get("tree"), len(m["indices"]))
+                if m.get("_visit_order") is None or len(m["_visit_order"]) != len(m["indices"]):
+                    m["_visit_order"] = reference_visit_order(m.get("tree"), len(m["indices"]))  # depends on the tree only
+                order = m["_visit_order"]
                 sc.add_mesh(m["positions"], m["normals"], m["texture_coords"], m["indices"][order])
                 perm.append(base + order)
                 base += len(order)
