@@ -13,10 +13,11 @@ def main(stage, resolution=(1280, 720), spp=8192, propagate_limit=32):
     spp = int(os.environ.get("LPT_SPP", spp))
     world, camera = scenes.SCENES[stage](resolution)
     start_time = time.time()
-    bsdf = {"5_anti_aliasing": NormalColor, "6_diffuse": DiffuseBSDF}.get(stage, DielectricBSDF)
-    # stage 5 writes the linear image (no post_processing() in that script)
-    image, stats = render(world, camera, spp=spp, propagate_limit=propagate_limit, bsdf=bsdf, return_stats=True,
-                          postprocess=stage != "5_anti_aliasing")
+    early = stage in ("2_camera_and_ray", "3_adding_a_sphere", "4_objects")  # one lattice ray per pixel, normals / sky
+    bsdf = {"5_anti_aliasing": NormalColor, "6_diffuse": DiffuseBSDF}.get(stage, NormalColor if early else DielectricBSDF)
+    # stages <= 5 write the linear image (no post_processing() in those scripts)
+    image, stats = render(world, camera, spp=1 if early else spp, propagate_limit=propagate_limit, bsdf=bsdf, return_stats=True,
+                          postprocess=not early and stage != "5_anti_aliasing", pixel_grid=early)
     print(f"Time elapsed: {time.time() - start_time:.2f}s  ({stats.paths / stats.ms_total / 1e3:.0f} Mpaths/s)")
     os.makedirs("outputs", exist_ok=True)
     imwrite(image, f"outputs/{stage}.png")

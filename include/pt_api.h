@@ -60,6 +60,8 @@ extern "C" {
 #define PT_FLAG_ACCUM_SQ 1      /* also accumulate per-pixel sum of squares (needs accum_sq != NULL)   */
 #define PT_FLAG_TIMING 2        /* record CUDA events around every kernel launch (fills PtStats.ms_*)  */
 #define PT_FLAG_COUNTERS 4      /* count BVH nodes visited / primitives tested (slower)                */
+#define PT_FLAG_PIXEL_GRID 64   /* stages 2-4 camera (2_camera_and_ray/camera.py:67): the ray of pixel (i, j) goes through
+                                   the lattice point (i/(W-1), j/(H-1)) of the view rectangle, no jitter (W, H >= 2)    */
 /* pt_trace_batch_device flags */
 #define PT_FLAG_NO_SORT 8       /* keep the batch order (default: batches >= 65536 rays are traced in an
                                    entry-point/direction Morton order; results always land in batch order) */

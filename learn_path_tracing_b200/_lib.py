@@ -23,6 +23,7 @@ PT_SHADE_V2_NORMALS = 3
 PT_FLAG_ACCUM_SQ = 1
 PT_FLAG_TIMING = 2
 PT_FLAG_COUNTERS = 4
+PT_FLAG_PIXEL_GRID = 64  # stages 2-4 camera: lattice rays i/(W-1), j/(H-1), no jitter
 
 PT_MODE_AUTO = 0
 PT_MODE_SPLIT = 1   # classic wavefront: k_extend + k_shade per bounce, pool refilled by an atomic counter

@@ -286,11 +286,12 @@ PT_DEV void scatter_legacy(const SceneView& sv, PathState& p, const Hit& h, floa
 struct CameraDev {
     float3 pos, front, right, up;
     float view_w, view_h, focal, aperture;
-    float inv_w, inv_h;  // 1/width, 1/height
+    float inv_w, inv_h;  // 1/width, 1/height (PT_FLAG_PIXEL_GRID: 1/(width-1), 1/(height-1))
+    float jitter;        // 1 (pixel jitter, camera.py:88) or 0 (PT_FLAG_PIXEL_GRID); x * 1.0f is exact
 };
 PT_DEV void camera_ray(const CameraDev& c, int i, int j, float4 u, float3* o, float3* d) {
-    const float fx = ((float)i + u.x) * c.inv_w - 0.5f;
-    const float fy = ((float)j + u.y) * c.inv_h - 0.5f;
+    const float fx = ((float)i + u.x * c.jitter) * c.inv_w - 0.5f;
+    const float fy = ((float)j + u.y * c.jitter) * c.inv_h - 0.5f;
     const float3 target = c.focal * (c.front + (fx * c.view_w) * c.right + (fy * c.view_h) * c.up);
     if (c.aperture == 0.0f) {  // pinhole (warp-uniform): the lens sample is multiplied by zero in the reference, skip it
         *o = c.pos;

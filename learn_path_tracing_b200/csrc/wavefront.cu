@@ -288,7 +288,7 @@ __global__ void k_random_rays(float4* rays, long long n, uint32_t seed) {
 }
 
 // ------------------------------------------------------------------------------------------------
-static CameraDev make_camera(const PtCamera* c, int W, int H) {
+static CameraDev make_camera(const PtCamera* c, int W, int H, bool grid = false) {
     CameraDev d;
     d.pos = make_float3(c->pos[0], c->pos[1], c->pos[2]);
     d.front = make_float3(c->front[0], c->front[1], c->front[2]);
@@ -296,7 +296,8 @@ static CameraDev make_camera(const PtCamera* c, int W, int H) {
     d.up = make_float3(c->up[0], c->up[1], c->up[2]);
     d.view_w = c->view_w; d.view_h = c->view_h;
     d.focal = c->focal_length; d.aperture = c->aperture;
-    d.inv_w = 1.0f / (float)W; d.inv_h = 1.0f / (float)H;
+    d.inv_w = 1.0f / (float)(grid ? W - 1 : W); d.inv_h = 1.0f / (float)(grid ? H - 1 : H);
+    d.jitter = grid ? 0.0f : 1.0f;
     return d;
 }
 
@@ -442,6 +443,7 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
     const bool legacy = p->shading_model == PT_SHADE_LEGACY;
     PT_REQUIRE(legacy || (s->view.n_tri == 0 && !s->view.legacy_spheres), "v2 shading models need a v2 sphere scene");
     PT_REQUIRE(!legacy || s->view.n_sph == 0 || s->view.legacy_spheres, "legacy shading needs legacy (textured) spheres");
+    PT_REQUIRE(!(p->flags & PT_FLAG_PIXEL_GRID) || (p->width >= 2 && p->height >= 2), "PT_FLAG_PIXEL_GRID needs width, height >= 2");
     const bool want_sq = (p->flags & PT_FLAG_ACCUM_SQ) != 0;
     PT_REQUIRE(!want_sq || accum_sq_dev, "PT_FLAG_ACCUM_SQ needs accum_sq");
     PT_REQUIRE(p->reserved[0] >= 0 && p->reserved[0] <= 5, "reserved[0] (wavefront mode) must be 0 ... 5");
@@ -465,7 +467,7 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
     if (rc_pool) return rc_pool;
 
     RenderConsts rc;
-    rc.cam = make_camera(cam, p->width, p->height);
+    rc.cam = make_camera(cam, p->width, p->height, (p->flags & PT_FLAG_PIXEL_GRID) != 0);
     rc.total_paths = total;
     rc.W = p->width; rc.H = p->height;
     rc.seed = p->seed; rc.spp_offset = (uint32_t)p->spp_offset;

@@ -24,6 +24,23 @@ def _six_spheres(with_glass=True, ground_y=-10000.5):
     return [s1, s2, s3, s4, s5, ground]
 
 
+def scene_2_camera_and_ray(resolution=(1280, 720)):
+    """2_camera_and_ray/__main__.py:26-28 — no world at all, the camera pitched up by 30 degrees looks at the sky.
+    (A scene cannot be empty here; the one sphere sits behind the camera where no ray can meet it.)"""
+    w = World([Sphere(Vec3f([0.0, -10.0, 10.0]), 0.5)])
+    cam = Camera(resolution)
+    cam.set_direction(0, 30, 0)
+    return w, cam
+
+
+def scene_3_adding_a_sphere(resolution=(1280, 720)):
+    """3_adding_a_sphere/__main__.py:27-38,49-51 — one sphere two units in front of a camera at the origin."""
+    w = World([Sphere(Vec3f([0.0, 0.0, -2.0]), 0.5)])
+    cam = Camera(resolution)
+    cam.set_direction(0, 0)
+    return w, cam
+
+
 def scene_5_anti_aliasing(resolution=(1280, 720)):
     """5_anti_aliasing/__main__.py:44-50 (also 4_objects) — two plain spheres, normals shown as colours."""
     w = World([Sphere(Vec3f([0.0, 0.0, 0.0]), 0.5), Sphere(Vec3f([0, -100.5, 0]), 100)])
@@ -107,5 +124,7 @@ def scene_10_final(resolution=(1280, 720), seed=20261018):
     return random_scene(seed=seed), cam
 
 
-SCENES = {"5_anti_aliasing": scene_5_anti_aliasing, "6_diffuse": scene_6_diffuse, "7_reflect": scene_7_reflect, "8_refract": scene_8_refract,
+# stages 2-4 shoot one ray per pixel through the lattice i/(W-1), j/(H-1) (render(..., pixel_grid=True), spp=1)
+SCENES = {"2_camera_and_ray": scene_2_camera_and_ray, "3_adding_a_sphere": scene_3_adding_a_sphere,
+          "4_objects": scene_5_anti_aliasing, "5_anti_aliasing": scene_5_anti_aliasing, "6_diffuse": scene_6_diffuse, "7_reflect": scene_7_reflect, "8_refract": scene_8_refract,
           "9_dof": scene_9_dof, "10_final": scene_10_final}

@@ -61,10 +61,14 @@ void orc_rng4(uint32_t pixel, uint32_t sample, uint32_t stream, uint32_t seed, f
 /* ------------------------------------------------------------------------------------------ */
 /* camera — ref: v2 camera.py:29-35 (sample_in_disk), :71-93 (get_rays); legacy:438-453        */
 /* ------------------------------------------------------------------------------------------ */
-static inline void camera_ray(const PtCamera* c, int W, int H, int i, int j, const float u[4], V3* ro, V3* rd) {
+static inline void camera_ray(const PtCamera* c, int W, int H, int i, int j, const float u[4], int grid, V3* ro, V3* rd) {
     V3 dir = vload(c->front), wa = vload(c->right), ha = vload(c->up), pos = vload(c->pos);
     float fx = ((float)i + u[0]) / (float)W - 0.5f; /* camera.py:88 */
     float fy = ((float)j + u[1]) / (float)H - 0.5f;
+    if (grid) { /* stages 2-4, 2_camera_and_ray/camera.py:67: i / (width - 1) - 0.5, no jitter */
+        fx = (float)i / (float)(W - 1) - 0.5f;
+        fy = (float)j / (float)(H - 1) - 0.5f;
+    }
     V3 target = vscale(vadd(vadd(dir, vscale(wa, fx * c->view_w)), vscale(ha, fy * c->view_h)), c->focal_length);
     float r = sqrtf(u[2]); /* camera.py:31-34 */
     float theta = 2.0f * ORC_PI * u[3];
@@ -82,7 +86,7 @@ void orc_generate_rays(const PtCamera* cam, int width, int height, int sample, u
             float u[4];
             orc_rng4(pix, (uint32_t)sample, 0u, seed, u);
             V3 ro, rd;
-            camera_ray(cam, width, height, i, j, u, &ro, &rd);
+            camera_ray(cam, width, height, i, j, u, 0, &ro, &rd);
             float* r = rays + (size_t)pix * 8;
             r[0] = ro.x; r[1] = ro.y; r[2] = ro.z; r[3] = ORC_EPS;
             r[4] = rd.x; r[5] = rd.y; r[6] = rd.z; r[7] = INFINITY;
@@ -529,6 +533,7 @@ int orc_render(const OrcScene* sc, const PtCamera* cam, const PtRenderParams* p,
                PtStats* stats, int threads) {
     const int W = p->width, H = p->height;
     if (W <= 0 || H <= 0 || p->spp < 0 || p->max_depth <= 0) return PT_ERR_INVALID;
+    if ((p->flags & PT_FLAG_PIXEL_GRID) && (W < 2 || H < 2)) return PT_ERR_INVALID;
     init_luts();
 #ifdef _OPENMP
     if (threads > 0) omp_set_num_threads(threads);
@@ -546,7 +551,7 @@ int orc_render(const OrcScene* sc, const PtCamera* cam, const PtRenderParams* p,
                 float u[4], u2[4];
                 orc_rng4(pix, sample, 0u, p->seed, u);
                 V3 ro, rd, l = v3(1.0f, 1.0f, 1.0f);
-                camera_ray(cam, W, H, i, j, u, &ro, &rd);
+                camera_ray(cam, W, H, i, j, u, (p->flags & PT_FLAG_PIXEL_GRID) != 0, &ro, &rd);
                 int ended = 0;
                 V3 radiance = v3(0, 0, 0);
                 for (int b = 0; b < p->max_depth; ++b) {

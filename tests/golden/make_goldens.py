@@ -15,6 +15,8 @@ import numpy as np
 from PIL import Image
 
 STAGES = ["5_anti_aliasing", "6_diffuse", "7_reflect", "8_refract", "9_dof"]
+# stages 2-4 are deterministic (one lattice ray per pixel, no random numbers): kept at their native size as exact pins
+EXACT = ["1_save_img", "2_camera_and_ray", "3_adding_a_sphere", "4_objects"]   # stage 1 pins imwrite alone
 
 
 def main(ref="/root/reference"):
@@ -29,6 +31,11 @@ def main(ref="/root/reference"):
             b = a.reshape(h // 4, 4, w // 4, 4, 3).mean(axis=(1, 3))
         out = os.path.join(here, f"{s}_320x180.png")
         Image.fromarray(np.round(b).astype(np.uint8)).save(out, optimize=True)
+        print(out, os.path.getsize(out), "bytes")
+    for s in EXACT:
+        im = Image.open(os.path.join(ref, "outputs", s + ".png")).convert("RGB")
+        out = os.path.join(here, f"{s}_{im.size[0]}x{im.size[1]}.png")
+        im.save(out, optimize=True)
         print(out, os.path.getsize(out), "bytes")
 
 

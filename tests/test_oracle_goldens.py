@@ -47,6 +47,47 @@ def test_oracle_matches_reference_stage5_normals(oracle):
     assert float(np.sqrt(((img[::-1] - gold) ** 2).mean())) > 20  # a vertically flipped image is far off
 
 
+EXACT = [("2_camera_and_ray", 1280, 720), ("3_adding_a_sphere", 1280, 720), ("4_objects", 320, 180)]
+
+
+@pytest.mark.parametrize("name,W,H", EXACT)
+def test_oracle_reproduces_the_deterministic_stages_exactly(oracle, name, W, H):
+    """outputs/{2_camera_and_ray,3_adding_a_sphere,4_objects}.png use no random numbers (one ray per pixel through the
+    lattice i/(W-1), j/(H-1), 2_camera_and_ray/camera.py:67): noise-free known answers for rotate() incl. a 30 degree
+    pitch, the field-of-view geometry, Sphere.hit / World.hit, the normal, the sky gradient and imwrite's orientation
+    and uint8 quantisation.  The oracle must reproduce them to the byte, up to a last-ulp flip at a quantisation
+    threshold (measured: 99.997-99.9998 % of the bytes equal, never off by more than 1)."""
+    world, cam = scenes.SCENES[name]((W, H))
+    acc, _, st = oracle.render(oracle.scene_from_world(world), cam.to_struct(), W, H, 1, 32, L.PT_SHADE_V2_NORMALS, seed=1,
+                               flags=L.PT_FLAG_PIXEL_GRID)
+    img = L.to_uint8(acc).astype(np.int32)
+    gold = np.asarray(Image.open(os.path.join(GOLDEN, f"{name}_{W}x{H}.png")).convert("RGB"), np.int32)
+    d = np.abs(img - gold)
+    assert st.paths == st.segments == W * H
+    assert d.max() <= 1, d.max()
+    assert (d == 0).mean() > 0.9999, (d == 0).mean()
+    assert np.abs(img[::-1] - gold).mean() > 3      # orientation matters
+
+
+def test_imwrite_reproduces_stage1_png_exactly():
+    """outputs/1_save_img.png: image[i, j] = (i/256, j/256, 0) through ti.tools.imwrite (1_save_img/__main__.py:10-19) pins
+    the field orientation (x right, y up) and the truncating uint8 cast of our imwrite/to_uint8 to the byte."""
+    i, j = np.meshgrid(np.arange(256), np.arange(256), indexing="ij")
+    field = np.stack([i / 256, j / 256, np.zeros_like(i, float)], -1).astype(np.float32)
+    gold = np.asarray(Image.open(os.path.join(GOLDEN, "1_save_img_256x256.png")).convert("RGB"))
+    assert np.array_equal(L.to_uint8(field), gold)
+    assert np.array_equal(L.to_uint8(L.imread(os.path.join(GOLDEN, "1_save_img_256x256.png"))), gold)  # imread inverts it
+
+
+def test_pixel_grid_is_independent_of_seed_and_sample(oracle):
+    world, cam = scenes.scene_3_adding_a_sphere((64, 36))
+    a, _, _ = oracle.render(oracle.scene_from_world(world), cam.to_struct(), 64, 36, 1, 32, L.PT_SHADE_V2_NORMALS, seed=1,
+                            flags=L.PT_FLAG_PIXEL_GRID)
+    b, _, _ = oracle.render(oracle.scene_from_world(world), cam.to_struct(), 64, 36, 1, 32, L.PT_SHADE_V2_NORMALS, seed=77,
+                            spp_offset=5, flags=L.PT_FLAG_PIXEL_GRID)
+    assert np.array_equal(a, b)
+
+
 def test_segments_per_path_matches_survey(oracle):
     """8_refract averages 2.33 ray segments per path."""
     world, cam = scenes.scene_8_refract((160, 90))
