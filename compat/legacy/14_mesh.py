@@ -10,7 +10,7 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
-from learn_path_tracing_b200 import imwrite  # noqa: E402
+from learn_path_tracing_b200 import imwrite_legacy as imwrite  # noqa: E402  (the legacy ti.imwrite rounds)
 from learn_path_tracing_b200.legacy import Camera, LegacyRenderer, TextureManager, Vec3f, World  # noqa: E402
 
 resolution = (3000, 2000)

@@ -10,7 +10,7 @@ from ._lib import (PT_MODE_AUTO, PT_MODE_FUSED, PT_MODE_SPLIT, PT_MODE_PERSIST, 
 from .bsdf import DielectricBSDF, DiffuseBSDF, MetalBSDF, NormalColor
 from .camera import Camera
 from .dtypes import HitRecord, Mat3f, Material, Ray, Sphere, Vec2f, Vec2i, Vec3f
-from .image_io import imread, imwrite, to_uint8
+from .image_io import imread, imwrite, imwrite_legacy, to_uint8
 from .postprocessing import ACES_tonemapping, gamma_correction
 from .multigpu import reduce_accumulators, render_distributed, split_samples
 from .render import Renderer, default_context, render
@@ -19,6 +19,6 @@ from .world import World
 __all__ = [
     "Context", "Scene", "PtError", "Camera", "World", "Sphere", "Material", "Ray", "HitRecord", "Vec2f", "Vec2i",
     "Vec3f", "Mat3f", "MetalBSDF", "DielectricBSDF", "DiffuseBSDF", "NormalColor", "ACES_tonemapping", "gamma_correction",
-    "Renderer", "render", "default_context", "render_distributed", "split_samples", "reduce_accumulators", "imwrite", "imread", "to_uint8", "PT_SHADE_V2", "PT_SHADE_V2_DIFFUSE", "PT_SHADE_V2_NORMALS",
+    "Renderer", "render", "default_context", "render_distributed", "split_samples", "reduce_accumulators", "imwrite", "imwrite_legacy", "imread", "to_uint8", "PT_SHADE_V2", "PT_SHADE_V2_DIFFUSE", "PT_SHADE_V2_NORMALS",
     "PT_SHADE_LEGACY", "PT_FLAG_ACCUM_SQ", "PT_FLAG_TIMING", "PT_FLAG_COUNTERS", "PT_FLAG_PIXEL_GRID", "PT_MODE_AUTO", "PT_MODE_SPLIT", "PT_MODE_FUSED", "PT_MODE_PERSIST", "PT_MODE_QUEUE", "PT_MODE_DUAL", "PT_FLAG_NO_SORT", "PT_FLAG_TRACE_SIMPLE", "PT_FLAG_NO_QNODES",
 ]

@@ -32,6 +32,13 @@ def main(ref="/root/reference"):
         out = os.path.join(here, f"{s}_320x180.png")
         Image.fromarray(np.round(b).astype(np.uint8)).save(out, optimize=True)
         print(out, os.path.getsize(out), "bytes")
+    # the legacy tutorial stages with the legacy camera (half-angle fov, 15_module.py:397-401 has the same formula):
+    # 3 and 4 are deterministic lattice renders, 5 is 100 spp of normals as colours
+    for s in ["3_adding_a_sphere", "4_objects", "5_anti_aliasing"]:
+        im = Image.open(os.path.join(ref, "legacy", "PT_in_one_weekend", s + ".png")).convert("RGB")
+        out = os.path.join(here, f"legacy_{s}_{im.size[0]}x{im.size[1]}.png")
+        im.save(out, optimize=True)
+        print(out, os.path.getsize(out), "bytes")
     for s in EXACT:
         im = Image.open(os.path.join(ref, "outputs", s + ".png")).convert("RGB")
         out = os.path.join(here, f"{s}_{im.size[0]}x{im.size[1]}.png")

@@ -69,6 +69,45 @@ def test_oracle_reproduces_the_deterministic_stages_exactly(oracle, name, W, H):
     assert np.abs(img[::-1] - gold).mean() > 3      # orientation matters
 
 
+def _legacy_stage(name, W, H):
+    """legacy/PT_in_one_weekend/{3_adding_a_sphere,4_objects,5_anti_aliasing}.py: camera at the origin looking down -z with
+    the LEGACY field of view (view_width = 2 tan(fov pi / 180), the formula 15_module.py:397-401 still uses)."""
+    from learn_path_tracing_b200 import Sphere, Vec3f, World, legacy
+    spheres = [Sphere(Vec3f([0.0, 0.0, -1.0]), 0.5)]
+    if name != "3_adding_a_sphere":
+        spheres.append(Sphere(Vec3f([0, -100.5, -1]), 100))
+    cam = legacy.Camera((W, H), fov=60)
+    cam.set_direction(0, 0)
+    return World(spheres), cam
+
+
+@pytest.mark.parametrize("name", ["3_adding_a_sphere", "4_objects"])
+def test_oracle_reproduces_the_legacy_deterministic_stages_to_the_byte(oracle, name):
+    """The legacy tutorial's lattice renders pin the legacy camera's half-angle field of view and the ROUNDING cast of
+    the old ti.imwrite (measured: every byte of both 400x225 PNGs equal; the truncating cast of v2 matches only 51-64 %)."""
+    W, H = 400, 225
+    world, cam = _legacy_stage(name, W, H)
+    acc, _, _ = oracle.render(oracle.scene_from_world(world), cam.to_struct(), W, H, 1, 32, L.PT_SHADE_V2_NORMALS, seed=1,
+                              flags=L.PT_FLAG_PIXEL_GRID)
+    gold = np.asarray(Image.open(os.path.join(GOLDEN, f"legacy_{name}_{W}x{H}.png")).convert("RGB"), np.int32)
+    d = np.abs(L.to_uint8(acc, rounding=True).astype(np.int32) - gold)
+    assert d.max() <= 1 and (d == 0).mean() > 0.9999, (d.max(), (d == 0).mean())
+    assert (L.to_uint8(acc).astype(np.int32) == gold).mean() < 0.7   # the v2 cast is NOT what the legacy ti.imwrite did
+
+
+def test_oracle_matches_legacy_stage5_with_the_rounding_cast(oracle):
+    """legacy 5_anti_aliasing.png (400x225, 100 spp, jittered legacy camera): unbiased with the rounding cast (measured
+    bias -0.0001, rmse 0.46), half a level dark with the truncating one."""
+    W, H, SPP = 400, 225, 128
+    world, cam = _legacy_stage("5_anti_aliasing", W, H)
+    acc, _, _ = oracle.render(oracle.scene_from_world(world), cam.to_struct(), W, H, SPP, 32, L.PT_SHADE_V2_NORMALS, seed=1)
+    gold = np.asarray(Image.open(os.path.join(GOLDEN, f"legacy_5_anti_aliasing_{W}x{H}.png")).convert("RGB"), np.float64)
+    d = L.to_uint8(acc / SPP, rounding=True).astype(np.float64) - gold
+    assert np.sqrt((d**2).mean()) < 1.0 and abs(d.mean()) < 0.1, (np.sqrt((d**2).mean()), d.mean())
+    dt = L.to_uint8(acc / SPP).astype(np.float64) - gold
+    assert dt.mean() < -0.3
+
+
 def test_imwrite_reproduces_stage1_png_exactly():
     """outputs/1_save_img.png: image[i, j] = (i/256, j/256, 0) through ti.tools.imwrite (1_save_img/__main__.py:10-19) pins
     the field orientation (x right, y up) and the truncating uint8 cast of our imwrite/to_uint8 to the byte."""
