@@ -198,11 +198,19 @@ class Context:
         check(self.lib.pt_generate_rays(self.handle, C.byref(cam), width, height, sample, seed, _fptr(rays)))
         return rays
 
-    def trace_batch(self, scene: "Scene", rays: np.ndarray, counters: bool = False):
+    def trace_batch(self, scene: "Scene", rays: np.ndarray, counters: bool = False, out=None):
+        """World.hit over a host ray batch [n,8] -> (prim ids, t, stats).  out=(ids int32[n], t float32[n]) reuses the
+        caller's result arrays (fresh numpy arrays cost a page fault per 4 KiB on their first write)."""
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
         n = rays.shape[0]
-        ids = np.empty(n, np.int32)
-        t = np.empty(n, np.float32)
+        if out is not None:
+            ids, t = out
+            if not (ids.dtype == np.int32 and t.dtype == np.float32 and ids.shape == (n,) and t.shape == (n,)
+                    and ids.flags.c_contiguous and t.flags.c_contiguous):
+                raise PtError("trace_batch: out must be (int32[n], float32[n]) contiguous arrays")
+        else:
+            ids = np.empty(n, np.int32)
+            t = np.empty(n, np.float32)
         st = PtStats()  # filled (and the counting kernel variant used) only when counters=True
         check(self.lib.pt_trace_batch(self.handle, scene.handle, _fptr(rays), n, _fptr(ids, np.int32), _fptr(t),
                                       C.byref(st) if counters else None))

@@ -64,9 +64,13 @@ extern "C" void pt_context_destroy(PtContext* c) {
         if (c->stage_rays_d[b]) cudaFree(c->stage_rays_d[b]);
         if (c->stage_hits_d[b]) cudaFree(c->stage_hits_d[b]);
         if (c->stage_ev[b]) cudaEventDestroy(c->stage_ev[b]);
+        if (c->stage_ev_in[b]) cudaEventDestroy(c->stage_ev_in[b]);
+        if (c->stage_ev_cmp[b]) cudaEventDestroy(c->stage_ev_cmp[b]);
         if (c->up_h[b]) cudaFreeHost(c->up_h[b]);
         if (c->up_ev[b]) cudaEventDestroy(c->up_ev[b]);
     }
+    if (c->stage_in) cudaStreamDestroy(c->stage_in);
+    if (c->stage_out) cudaStreamDestroy(c->stage_out);
     if (c->counters) cudaFree(c->counters);
     if (c->counters_host) cudaFreeHost(c->counters_host);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
@@ -624,8 +628,9 @@ extern "C" int pt_scene_triangles_download(const PtScene* s, float* tris, int64_
 
 // ---- host-buffer wrappers ----------------------------------------------------------------------
 // pt_trace_batch: host rays in, host ids/t out.  The batch is cut into chunks that go through a
-// double-buffered pipeline — a few CPU threads copy chunk k into pinned memory, the stream does H2D + sort + trace +
-// unpack (records -> ids | t) + D2H for it, and meanwhile the CPU copies the results of chunk k-1 out — so pageable caller memory never
+// double-buffered pipeline — a few CPU threads copy chunk k into pinned memory, a copy stream does its H2D, the context's
+// stream sort + trace + unpack (records -> ids | t), a second copy stream the D2H, and meanwhile the CPU copies the results
+// of chunk k-1 out: H2D(k+1), tracing(k) and D2H(k-1) overlap — so pageable caller memory never
 // meets cudaMemcpy directly and nothing is allocated per call (grow-only staging in the context).
 static int ensure_trace_staging(PtContext* ctx, int64_t chunk) {
     if (ctx->stage_chunk >= chunk) return PT_OK;
@@ -644,7 +649,11 @@ static int ensure_trace_staging(PtContext* ctx, int64_t chunk) {
         PT_CUDA(cudaMalloc(&ctx->stage_rays_d[b], (size_t)chunk * 32));
         PT_CUDA(cudaMalloc(&ctx->stage_hits_d[b], (size_t)chunk * 24));      // float4 records | ids | t
         if (!ctx->stage_ev[b]) PT_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[b], cudaEventDisableTiming));
+        if (!ctx->stage_ev_in[b]) PT_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev_in[b], cudaEventDisableTiming));
+        if (!ctx->stage_ev_cmp[b]) PT_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev_cmp[b], cudaEventDisableTiming));
     }
+    if (!ctx->stage_in) PT_CUDA(cudaStreamCreateWithFlags(&ctx->stage_in, cudaStreamNonBlocking));
+    if (!ctx->stage_out) PT_CUDA(cudaStreamCreateWithFlags(&ctx->stage_out, cudaStreamNonBlocking));
     ctx->stage_chunk = chunk;
     return PT_OK;
 }
@@ -680,9 +689,17 @@ extern "C" int pt_trace_batch(PtContext* ctx, const PtScene* s, const float* ray
         const int b = (int)(k & 1);
         if (k < n_chunks) {
             const int64_t lo = k * chunk, cnt = (lo + chunk <= n ? chunk : n - lo);
-            // buffer b was last used by chunk k-2, whose results were unpacked in iteration k-1
+            // buffers b (host and device) were last used by chunk k-2, whose D2H the host waited for in iteration k-1:
+            // everything of that chunk is over, no further events are needed for the reuse
             parallel_memcpy(ctx->stage_rays_h[b], rays_host + 8 * lo, (size_t)cnt * 32);
-            PT_CUDA(cudaMemcpyAsync(ctx->stage_rays_d[b], ctx->stage_rays_h[b], (size_t)cnt * 32, cudaMemcpyHostToDevice, st));
+            if (k == 0) {  // the copy stream starts after whatever the caller queued on the context's stream
+                PT_CUDA(cudaEventRecord(ctx->stage_ev_cmp[1], st));
+                PT_CUDA(cudaStreamWaitEvent(ctx->stage_in, ctx->stage_ev_cmp[1], 0));
+            }
+            PT_CUDA(cudaMemcpyAsync(ctx->stage_rays_d[b], ctx->stage_rays_h[b], (size_t)cnt * 32, cudaMemcpyHostToDevice,
+                                    ctx->stage_in));
+            PT_CUDA(cudaEventRecord(ctx->stage_ev_in[b], ctx->stage_in));
+            PT_CUDA(cudaStreamWaitEvent(st, ctx->stage_ev_in[b], 0));
             PtStats cs;
             rc = pt_trace_batch_device(ctx, s, ctx->stage_rays_d[b], cnt, ctx->stage_hits_d[b], stats ? PT_FLAG_COUNTERS : 0,
                                        stats ? &cs : nullptr);
@@ -696,8 +713,10 @@ extern "C" int pt_trace_batch(PtContext* ctx, const PtScene* s, const float* ray
             int32_t* ids_d = (int32_t*)((char*)ctx->stage_hits_d[b] + (size_t)chunk * 16);
             k_unpack_hits<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>((const float4*)ctx->stage_hits_d[b], cnt, ids_d,
                                                                          (float*)(ids_d + chunk));
-            PT_CUDA(cudaMemcpyAsync(ctx->stage_hits_h[b], ids_d, (size_t)chunk * 8, cudaMemcpyDeviceToHost, st));
-            PT_CUDA(cudaEventRecord(ctx->stage_ev[b], st));
+            PT_CUDA(cudaEventRecord(ctx->stage_ev_cmp[b], st));
+            PT_CUDA(cudaStreamWaitEvent(ctx->stage_out, ctx->stage_ev_cmp[b], 0));
+            PT_CUDA(cudaMemcpyAsync(ctx->stage_hits_h[b], ids_d, (size_t)chunk * 8, cudaMemcpyDeviceToHost, ctx->stage_out));
+            PT_CUDA(cudaEventRecord(ctx->stage_ev[b], ctx->stage_out));
         }
         if (k >= 1) {  // unpack chunk k-1 while the GPU works on chunk k
             const int pb = (int)((k - 1) & 1);

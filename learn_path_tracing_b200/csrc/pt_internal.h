@@ -87,6 +87,9 @@ struct PtContext {
     void *stage_rays_h[2] = {nullptr, nullptr}, *stage_hits_h[2] = {nullptr, nullptr};
     void *stage_rays_d[2] = {nullptr, nullptr}, *stage_hits_d[2] = {nullptr, nullptr};
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    // copy streams of that pipeline: H2D of chunk k+1 and D2H of chunk k-1 run beside the tracing of chunk k
+    cudaStream_t stage_in = nullptr, stage_out = nullptr;
+    cudaEvent_t stage_ev_in[2] = {nullptr, nullptr}, stage_ev_cmp[2] = {nullptr, nullptr};
     // large host -> device uploads (texture atlas): two pinned chunks filled by a few host threads while the copy
     // engine drains the other one
     void* up_h[2] = {nullptr, nullptr};
