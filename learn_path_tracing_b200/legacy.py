@@ -102,6 +102,8 @@ def load_obj(file_path, texture_start_id, flip_z=False, flip_textcoord=False, tr
     """15_module.py:135-206.  Triangles with full v/vt/vn triplets, 1-based indices; every `newmtl` maps to its
     map_Kd file, textures are de-duplicated by path and numbered from texture_start_id in first-seen order.
     Returns (positions [V,3], normals [N,3], texture_coords [T,2], indices [F,10] int32, textures list)."""
+    if not os.path.exists(file_path):  # the scripts hard-code './models/...': search the asset roots (SURVEY appendix E)
+        file_path = resolve_asset(file_path) or file_path
     dir_path = os.path.dirname(file_path)
     positions, normals, texture_coords, indices, textures = [], [], [], [], []
     textures_name = {}
