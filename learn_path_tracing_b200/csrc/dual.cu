@@ -11,9 +11,11 @@
 //
 //   finish    traversal done: hit record -> S.h, record becomes HIT or MISS
 //   miss      MISS records: sky / environment * throughput -> RED.v4, record becomes EMPTY
-//   hit       HIT records: scatter; the continued ray is written back (READY), or EMPTY at the depth limit
-//   regen     EMPTY records get the next camera path of the warp's work unit (fused ray generation), READY
-//   start     lanes that are not walking flip to a READY record and begin its traversal (the one trav_begin site)
+//   hit       HIT records: scatter; the continued ray is written back (RAW), or EMPTY at the depth limit
+//   regen     EMPTY records get the next camera path of the warp's work unit (fused ray generation), RAW
+//   prep      RAW records: inline spheres + global primitives are tested (first half of the segment), READY —
+//             or, in a tree-less scene, HIT / MISS at once: such scenes never walk, they only cycle these phases
+//   start     lanes that are not walking flip to a READY record and walk the tree for it
 //
 // Same RNG keys (pixel, sample, bounce) as every other mode: the same set of paths.
 #include <math.h>
@@ -27,10 +29,11 @@
 #define D_UNIT_SAMPLES 16
 
 #define PK_EMPTY 0
-#define PK_READY 1
-#define PK_HIT 2
-#define PK_MISS 3
-#define PK_WALK 4
+#define PK_RAW 1    // holds a ray (camera or scattered) whose segment has not been prepared yet
+#define PK_READY 2  // prepared (inline spheres / global primitives tested, result in S.h): waits to be walked
+#define PK_HIT 3
+#define PK_MISS 4
+#define PK_WALK 5
 
 struct DShared {  // two lane-private path records, one float4 column per field: conflict-free 128-bit accesses
     float4 a[2 * D_BLOCK];  // o.xyz | bits(pixel)
@@ -129,7 +132,7 @@ k_paths_dual(const SceneView sv, const RenderConsts rc, unsigned long long* __re
                             S.a[k] = make_float4(q.o.x, q.o.y, q.o.z, qa.w);
                             S.b[k] = make_float4(q.d.x, q.d.y, q.d.z, __uint_as_float(q.sample | (q.bounce << 24)));
                             S.c[k] = make_float4(q.l.x, q.l.y, q.l.z, 0.0f);
-                            ns = PK_READY;
+                            ns = PK_RAW;
                         }
                     }
                     if (cur) sc = ns; else so = ns;
@@ -175,7 +178,7 @@ k_paths_dual(const SceneView sv, const RenderConsts rc, unsigned long long* __re
                             S.a[k] = make_float4(co.x, co.y, co.z, __uint_as_float(pixel));
                             S.b[k] = make_float4(cd.x, cd.y, cd.z, __uint_as_float(sample));  // bounce 0
                             S.c[k] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-                            if (cur) sc = PK_READY; else so = PK_READY;
+                            if (cur) sc = PK_RAW; else so = PK_RAW;
                         }
                     }
                 }
@@ -183,16 +186,38 @@ k_paths_dual(const SceneView sv, const RenderConsts rc, unsigned long long* __re
             }
             __syncwarp();
         }
-        // start: a lane that is not walking flips to a READY record and begins its traversal
+        // prep: every ray made by the two phases above gets the first half of its segment — the inline spheres and the
+        // global primitives — HERE, with all the lanes that made one, not later when its lane gets to walk it (ncu on
+        // the first version: trav_begin at 7 of 32 lanes, a quarter of all instructions).  In a tree-less scene that is
+        // the whole segment: the record becomes HIT or MISS at once.
+        for (;;) {
+            const bool want = sc == PK_RAW || so == PK_RAW;
+            if (__ballot_sync(0xffffffffu, want) == 0u) break;
+            if (want) {
+                const bool cur = sc == PK_RAW;
+                const unsigned k = cur ? ci : ci ^ D_BLOCK;
+                const float4 qa = S.a[k], qb = S.b[k];
+                float best;
+                Hit hh;
+                trav_prep<COUNT>(sv, f3(qa), f3(qb), rc.tmin, INFINITY, best, hh, tc);
+                ++nseg;
+                S.h[k] = make_float4(best, __int_as_float(hh.prim), hh.u, hh.v);
+                const int ns = sv.root != PT_SENTINEL ? PK_READY : (hh.prim >= 0 ? PK_HIT : PK_MISS);
+                if (cur) sc = ns; else so = ns;
+            }
+            __syncwarp();
+        }
+        // start: a lane that is not walking flips to a READY record and walks the tree for it
         if (sc != PK_WALK && (sc == PK_READY || so == PK_READY)) {
             if (sc != PK_READY) {
                 ci ^= D_BLOCK;
                 const int t = sc; sc = so; so = t;
             }
-            const float4 qa = S.a[ci], qb = S.b[ci];
+            const float4 qa = S.a[ci], qb = S.b[ci], qh = S.h[ci];
             o = f3(qa); d = f3(qb);
-            trav_begin<COUNT>(sv, o, d, rc.tmin, INFINITY, T, stack, tc);
-            ++nseg;
+            T.best = qh.x;
+            T.h.t = qh.x; T.h.prim = __float_as_int(qh.y); T.h.u = qh.z; T.h.v = qh.w;
+            trav_start<COUNT>(sv, o, d, rc.tmin, T, stack, tc);
             sc = PK_WALK;
         }
         __syncwarp();

@@ -163,22 +163,30 @@ struct Trav {
     int sp;
 };
 
+// A segment begins in two halves: trav_prep tests what is not in the tree (inline spheres from the constant bank, the
+// few "global" primitives), trav_start sets up the walk of the tree with that result as the first bound.  The
+// persistent kernels do both at once (trav_begin); dual.cu prepares a ray where it is made (shading / regeneration
+// phases, many lanes) and starts it when its lane gets to it.
 template <bool COUNT>
-PT_DEV void trav_begin(const SceneView& sv, float3 o, float3 d, float tmin, float tmax, Trav& T, int* stack,
-                       TraceCounters& tc) {
-    T.h.t = -1.0f; T.h.prim = -1; T.h.u = 0.0f; T.h.v = 0.0f;
-    T.best = tmax;
+PT_DEV void trav_prep(const SceneView& sv, float3 o, float3 d, float tmin, float tmax, float& best, Hit& h,
+                      TraceCounters& tc) {
+    h.t = -1.0f; h.prim = -1; h.u = 0.0f; h.v = 0.0f;
+    best = tmax;
     for (int g = 0; g < sv.n_inl; ++g) {  // constant-bank operands, indexed
         if (COUNT) tc.prims++;
         float t;
         const int p = sv.inl_id[g];
         if (sphere_hit_ref(o, d, sv.inl_cr[g], sv.inl_r2[g], sv.inl_transparent[g] != 0, tmin, &t) && t >= tmin &&
-            (t < T.best || (t == T.best && p < T.h.prim))) {
-            T.best = t;
-            T.h.t = t; T.h.prim = p;
+            (t < best || (t == best && p < h.prim))) {
+            best = t;
+            h.t = t; h.prim = p;
         }
     }
-    for (int g = 0; g < sv.n_global; ++g) test_prim<COUNT>(sv, __ldg(&sv.global_prims[g]), o, d, tmin, T.h, T.best, tc);
+    for (int g = 0; g < sv.n_global; ++g) test_prim<COUNT>(sv, __ldg(&sv.global_prims[g]), o, d, tmin, h, best, tc);
+}
+
+template <bool COUNT>
+PT_DEV void trav_start(const SceneView& sv, float3 o, float3 d, float tmin, Trav& T, int* stack, TraceCounters& tc) {
     T.cur = sv.root;
     if (T.cur == PT_SENTINEL) return;  // tree-less scene (<= 8 primitives): the inline / global tests were everything
     T.inv = f3(1.0f / (fabsf(d.x) < 1e-18f ? copysignf(1e-18f, d.x) : d.x),
@@ -191,6 +199,13 @@ PT_DEV void trav_begin(const SceneView& sv, float3 o, float3 d, float tmin, floa
         test_prim<COUNT>(sv, ~T.cur, o, d, tmin, T.h, T.best, tc);
         T.cur = PT_SENTINEL;
     }
+}
+
+template <bool COUNT>
+PT_DEV void trav_begin(const SceneView& sv, float3 o, float3 d, float tmin, float tmax, Trav& T, int* stack,
+                       TraceCounters& tc) {
+    trav_prep<COUNT>(sv, o, d, tmin, tmax, T.best, T.h, tc);
+    trav_start<COUNT>(sv, o, d, tmin, T, stack, tc);
 }
 
 // 64-byte BVH2 node as two 256-bit loads (LDG.E.ENL2.256, new with sm_100): the L1 spends one tag
