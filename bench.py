@@ -283,7 +283,7 @@ def run_ours(args):
         n_ext = int(sum(s.launches_extend for s in stats))
         n_sh = int(sum(s.launches_shade for s in stats))
         if n_ext == 0:  # fused wavefront / persistent kernel: one kernel runs extend + shade + regeneration
-            kname = "k_paths_persist" if int(stats[0].reserved[0]) == 3 else "k_paths"
+            kname = {3: "k_paths_persist", 4: "k_paths_queue", 5: "k_paths_dual"}.get(int(stats[0].reserved[0]), "k_paths")
             bytes_k, ms_k, n_k = 160.0 * seg_rank0 + B_PER_PATH * paths_rank0, ms_sh, n_sh
         elif ms_sh >= ms_ext:
             kname, bytes_k, ms_k, n_k = "k_shade", B_SHADE_SEG * seg_rank0 + B_PER_PATH * paths_rank0, ms_sh, n_sh
@@ -474,9 +474,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="8_refract_1080p", choices=sorted(WORKLOADS) + sorted(INTERSECT))
-    ap.add_argument("--mode", type=int, default=0, help="wavefront mode: 0 auto (fused), 1 split kernels, 2 fused")
+    ap.add_argument("--mode", type=int, default=0, help="wavefront mode: 0 auto (= 3 persistent), 1 split kernels, 2 K-step fused, 3 persistent, 4 queue, 5 dual")
     ap.add_argument("--pool", type=int, default=0, help="path-pool slots (0 = library default)")
-    ap.add_argument("--k", type=int, default=0, help="fused mode: segments per launch (0 = default)")
+    ap.add_argument("--k", type=int, default=0, help="fused mode: segments per launch (0 = default); dual mode: blocks per SM (3 or 4)")
     ap.add_argument("--shade-min", type=int, default=0, help="persistent mode: waiting lanes that trigger shading (0 = default)")
     ap.add_argument("--serve-min", type=int, default=0, help="persistent mode: waiting lanes that trigger a service (0 = default)")
     ap.add_argument("--trace-flags", type=int, default=0, help="intersect workloads: PT_FLAG_* for pt_trace_batch_device")
