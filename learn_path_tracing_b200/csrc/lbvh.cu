@@ -7,9 +7,21 @@
 //   4. Karras 2012 hierarchy          (one thread per internal node, duplicate codes broken by index)
 //   5. bottom-up refit + emit         (second arrival at a node owns it; writes the 64-byte BVH2 node
 //                                      that stores BOTH child boxes, the layout traversal reads)
+//
+// For trees of up to PT_PLOC_MAX primitives step 4 is replaced by a locally-ordered agglomerative clustering over the
+// same Morton order (PLOC, Meister & Bittner 2018): every cluster looks PT_PLOC_RADIUS neighbours to either side for
+// the partner with the smallest merged surface area, mutual choices merge, the survivors are compacted, until one
+// cluster is left.  Same inputs and outputs as k_hierarchy (children / parent arrays), a better tree for the same
+// sort; the closest hit does not depend on the shape of the tree, so every parity test holds for both.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <stdlib.h>
+
+#include <utility>
 
 #include "pt_internal.h"
+
+#define PT_PLOC_MAX (1 << 20)  // larger trees keep the Karras hierarchy (one pass instead of ~30 rounds over all clusters)
 
 namespace {
 
@@ -146,6 +158,93 @@ __global__ void k_refit_emit(long long n, const int2* __restrict__ children, con
     }
 }
 
+// ---- PLOC ----------------------------------------------------------------------------------------
+#define PT_PLOC_RADIUS 16
+
+__global__ void k_ploc_init(long long n, const int* __restrict__ sorted_prim, const float4* __restrict__ aabb,
+                            int* __restrict__ ref, float4* __restrict__ lo, float4* __restrict__ hi) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int p = sorted_prim[i];
+    ref[i] = ~(int)i;  // leaf: sorted index, as k_hierarchy encodes it
+    lo[i] = aabb[2 * (size_t)p];
+    hi[i] = aabb[2 * (size_t)p + 1];
+}
+
+__device__ __forceinline__ float merged_area(float4 al, float4 ah, float4 bl, float4 bh) {
+    const float x = fmaxf(ah.x, bh.x) - fminf(al.x, bl.x), y = fmaxf(ah.y, bh.y) - fminf(al.y, bl.y),
+                z = fmaxf(ah.z, bh.z) - fminf(al.z, bl.z);
+    return x * y + y * z + z * x;
+}
+
+// nearest neighbour of every cluster within the radius: smallest merged area; ties go to the even/odd partner i^1 if it
+// is among them (a run of identical boxes — duplicated faces — then pairs up and halves every round instead of merging
+// once per round), else to the lowest index.  With that rule the lexicographically first of the globally closest pairs
+// is always mutual, so every round merges at least once.
+__global__ void k_ploc_nn(int c, const float4* __restrict__ lo, const float4* __restrict__ hi, int* __restrict__ nn) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    const float4 al = lo[i], ah = hi[i];
+    float best = INFINITY;
+    int bj = -1;
+    const int j0 = max(0, i - PT_PLOC_RADIUS), j1 = min(c - 1, i + PT_PLOC_RADIUS);
+    for (int j = j0; j <= j1; ++j) {
+        if (j == i) continue;
+        const float a = merged_area(al, ah, lo[j], hi[j]);
+        if (a < best || (a == best && j == (i ^ 1))) { best = a; bj = j; }
+    }
+    nn[i] = bj;
+}
+
+// mutual pairs merge into a new node (indices are handed out downwards: the very last merge, alone in its round,
+// gets 0 = the root); the lower partner carries the merged cluster on, the upper one drops out
+__global__ void k_ploc_merge(int c, long long n, const int* __restrict__ nn, int* __restrict__ ref, float4* __restrict__ lo,
+                             float4* __restrict__ hi, int* __restrict__ keep, int* __restrict__ next_node,
+                             int2* __restrict__ children, int* __restrict__ parent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    const int j = nn[i];
+    if (j < 0 || nn[j] != i) { keep[i] = 1; return; }
+    if (i > j) { keep[i] = 0; return; }
+    const int idx = atomicSub(next_node, 1);
+    const int ri = ref[i], rj = ref[j];
+    children[idx] = make_int2(ri, rj);
+    parent[ri < 0 ? (n - 1) + ~ri : ri] = idx;
+    parent[rj < 0 ? (n - 1) + ~rj : rj] = idx;
+    const float4 al = lo[i], ah = hi[i], bl = lo[j], bh = hi[j];
+    // nobody else reads lo/hi/ref of cluster i in this kernel (the neighbour search is over)
+    lo[i] = make_float4(fminf(al.x, bl.x), fminf(al.y, bl.y), fminf(al.z, bl.z), 0.0f);
+    hi[i] = make_float4(fmaxf(ah.x, bh.x), fmaxf(ah.y, bh.y), fmaxf(ah.z, bh.z), 0.0f);
+    ref[i] = idx;
+    keep[i] = 1;
+}
+
+__global__ void k_ploc_compact(int c, const int* __restrict__ keep, const int* __restrict__ pos, const int* __restrict__ ref,
+                               const float4* __restrict__ lo, const float4* __restrict__ hi, int* __restrict__ ref2,
+                               float4* __restrict__ lo2, float4* __restrict__ hi2, int* __restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    if (keep[i]) {
+        const int q = pos[i];
+        ref2[q] = ref[i]; lo2[q] = lo[i]; hi2[q] = hi[i];
+    }
+    if (i == c - 1) *count = pos[i] + keep[i];
+}
+
+// SAH cost of an emitted tree up to constants: the sum of the surface areas of every child box
+__global__ void k_sah_cost(const float4* __restrict__ nodes, long long n_nodes, double* __restrict__ cost) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double a = 0.0;
+    if (i < n_nodes) {
+        const float4 p = nodes[4 * i], q = nodes[4 * i + 1], r = nodes[4 * i + 2];
+        const float x0 = p.w - p.x, y0 = q.x - p.y, z0 = q.y - p.z;   // child 0: min p.xyz max p.w q.x q.y
+        const float x1 = r.y - q.z, y1 = r.z - q.w, z1 = r.w - r.x;   // child 1: min q.z q.w r.x max r.yzw
+        a = (double)(x0 * y0 + y0 * z0 + z0 * x0) + (double)(x1 * y1 + y1 * z1 + z1 * x1);
+    }
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0 && a != 0.0) atomicAdd(cost, a);
+}
+
 // Quantised copy of the nodes for big trees: child boxes as u16 in the root frame, conservative (a min never
 // dequantises above the float min, a max never below the float max, checked with the traversal's own fmaf).
 __device__ __forceinline__ unsigned q_down(float v, float lo, float scale) {
@@ -223,15 +322,87 @@ int pt_lbvh_build(PtContext* ctx, const float4* d_prim_aabb, const int* d_local_
     PT_CUDA(sc.alloc((char**)&tmp, tmp_bytes));
     PT_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, kb, vb, (int)n, 0, 63, st));
 
-    PT_CUDA(cudaMemsetAsync(flags, 0, (size_t)(n - 1) * sizeof(int), st));
-    k_hierarchy<<<(unsigned)((n - 1 + B - 1) / B), B, 0, st>>>(kb.Current(), n, children, parent);
-    k_refit_emit<<<gridN, B, 0, st>>>(n, children, parent, vb.Current(), d_prim_aabb, node_box, flags, nodes);
-    cudaError_t e = cudaStreamSynchronize(st);
-    if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) {
+    // PLOC scratch
+    int *ref[2] = {nullptr, nullptr}, *nn = nullptr, *keep = nullptr, *pos = nullptr, *ctl = nullptr;
+    float4 *lo[2] = {nullptr, nullptr}, *hi[2] = {nullptr, nullptr};
+    void* scan_tmp = nullptr;
+    size_t scan_bytes = 0;
+    double* d_cost = nullptr;
+    PT_CUDA(sc.alloc(&d_cost, 2));
+
+    // one hierarchy (Karras or PLOC) + refit into `out`; its SAH cost (sum of all child-box areas) into d_cost[slot]
+    auto build = [&](bool ploc, float4* out, int slot) -> int {
+        PT_CUDA(cudaMemsetAsync(flags, 0, (size_t)(n - 1) * sizeof(int), st));
+        if (ploc) {
+            if (!nn) {
+                for (int b = 0; b < 2; ++b) {
+                    PT_CUDA(sc.alloc(&ref[b], (size_t)n));
+                    PT_CUDA(sc.alloc(&lo[b], (size_t)n));
+                    PT_CUDA(sc.alloc(&hi[b], (size_t)n));
+                }
+                PT_CUDA(sc.alloc(&nn, (size_t)n));
+                PT_CUDA(sc.alloc(&keep, (size_t)n));
+                PT_CUDA(sc.alloc(&pos, (size_t)n));
+                PT_CUDA(sc.alloc(&ctl, 2));  // [0] next node index, [1] cluster count after the round
+                PT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, keep, pos, (int)n, st));
+                PT_CUDA(sc.alloc((char**)&scan_tmp, scan_bytes));
+            }
+            const int ctl0[2] = {(int)(n - 2), (int)n};
+            PT_CUDA(cudaMemcpyAsync(ctl, ctl0, sizeof ctl0, cudaMemcpyHostToDevice, st));
+            k_ploc_init<<<gridN, B, 0, st>>>(n, vb.Current(), d_prim_aabb, ref[0], lo[0], hi[0]);
+            int c = (int)n, cur = 0, rounds = 0;
+            while (c > 1) {
+                const unsigned g = (unsigned)((c + B - 1) / B);
+                k_ploc_nn<<<g, B, 0, st>>>(c, lo[cur], hi[cur], nn);
+                k_ploc_merge<<<g, B, 0, st>>>(c, n, nn, ref[cur], lo[cur], hi[cur], keep, ctl, children, parent);
+                PT_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, keep, pos, c, st));
+                k_ploc_compact<<<g, B, 0, st>>>(c, keep, pos, ref[cur], lo[cur], hi[cur], ref[cur ^ 1], lo[cur ^ 1], hi[cur ^ 1], ctl + 1);
+                int c_new = 0;
+                PT_CUDA(cudaMemcpyAsync(&c_new, ctl + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+                PT_CUDA(cudaStreamSynchronize(st));
+                if (c_new >= c || ++rounds > 4096) {  // cannot happen (the closest pair is always mutual)
+                    pt_set_error("pt_lbvh_build: PLOC made no progress (%d -> %d clusters)", c, c_new);
+                    return PT_ERR_CUDA;
+                }
+                c = c_new;
+                cur ^= 1;
+            }
+            const int minus1 = -1;
+            PT_CUDA(cudaMemcpy(parent, &minus1, sizeof(int), cudaMemcpyHostToDevice));  // the root (node 0) has no parent
+        } else {
+            k_hierarchy<<<(unsigned)((n - 1 + B - 1) / B), B, 0, st>>>(kb.Current(), n, children, parent);
+        }
+        k_refit_emit<<<gridN, B, 0, st>>>(n, children, parent, vb.Current(), d_prim_aabb, node_box, flags, out);
+        k_sah_cost<<<(unsigned)((n - 1 + B - 1) / B), B, 0, st>>>(out, n - 1, d_cost + slot);
+        PT_CUDA(cudaStreamSynchronize(st));
+        PT_CUDA(cudaGetLastError());
+        return PT_OK;
+    };
+
+    // Which hierarchy: PT_BUILDER=lbvh|ploc forces one (A/B runs).  Otherwise trees of up to PT_PLOC_MAX primitives are
+    // built BOTH ways (a millisecond each at these sizes) and the one with the lower SAH cost is kept — PLOC wins on the
+    // triangle meshes (Yoimiya 8.3 instead of 9.6 node visits per segment), the Karras tree on the RTIOW sphere field.
+    const char* env = getenv("PT_BUILDER");
+    const bool force = env && env[0];
+    PT_CUDA(cudaMemsetAsync(d_cost, 0, 2 * sizeof(double), st));
+    int rcb;
+    if (force || n > PT_PLOC_MAX) {
+        rcb = build(force && env[0] == 'p', nodes, 0);
+    } else {
+        float4* nodes2 = nullptr;
+        cudaError_t ea = cudaMalloc(&nodes2, (size_t)(n - 1) * 4 * sizeof(float4));
+        if (ea != cudaSuccess) { cudaFree(nodes); PT_CUDA(ea); }
+        rcb = build(false, nodes, 0);
+        if (rcb == PT_OK) rcb = build(true, nodes2, 1);
+        double cost[2] = {0.0, 0.0};
+        if (rcb == PT_OK && cudaMemcpy(cost, d_cost, sizeof cost, cudaMemcpyDeviceToHost) != cudaSuccess) rcb = PT_ERR_CUDA;
+        if (getenv("PT_BUILD_VERBOSE")) fprintf(stderr, "[libb200pt] %lld prims: SAH cost lbvh %.6g, ploc %.6g\n", (long long)n, cost[0], cost[1]);
+        if (rcb == PT_OK && cost[1] < cost[0]) std::swap(nodes, nodes2);
+        cudaFree(nodes2);
+    }
+    if (rcb) {
         cudaFree(nodes);
-        pt_set_error("pt_lbvh_build: %s", cudaGetErrorString(e));
-        return PT_ERR_CUDA;
+        return rcb;
     }
     *d_nodes_out = nodes;
     *n_nodes_out = n - 1;

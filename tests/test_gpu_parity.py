@@ -286,6 +286,48 @@ def test_random_triangles_match_bruteforce_oracle(ctx, oracle):
     assert st.nodes_visited > 0 and st.prims_tested > 0
 
 
+def _tree_stats(nodes, n_prims):
+    """(max depth, leaves seen once each?) of a downloaded BVH2 (nodes [N,16], refs at floats 12, 13)."""
+    kids = nodes[:, 12:14].copy().view(np.int32)
+    depth = np.zeros(nodes.shape[0], np.int64)
+    seen = np.zeros(n_prims, np.int64)
+    order = [0]
+    for i in order:          # breadth-first: parents before children
+        for c in kids[i]:
+            if c >= 0:
+                depth[c] = depth[i] + 1
+                order.append(int(c))
+            else:
+                seen[~c] += 1
+    return int(depth.max()) + 1, len(order) == nodes.shape[0] and bool((seen == 1).all())
+
+
+@pytest.mark.parametrize("builder", ["ploc", "lbvh", ""])   # "": both are built, the lower SAH cost is kept
+def test_tree_builders_are_valid_and_equivalent(ctx, oracle, builder, monkeypatch):
+    """Both hierarchy builders (Karras LBVH, PLOC over the same Morton order) emit a proper binary tree over every
+    primitive, shallow enough for the 64-entry traversal stack — also with thousands of exactly duplicated triangles
+    (the Genshin models double their two-sided faces) — and the closest hits do not depend on which one built it."""
+    monkeypatch.setenv("PT_BUILDER", builder)
+    tris = oracle.random_triangles(30000, 99, 0.03)
+    tris[20000:] = tris[123]                       # 10000 exact copies of one triangle
+    tris[10000:20000] = tris[:10000]               # and 10000 faces doubled
+    rays = oracle.random_rays(20000, 7)
+    sc = L.Scene(ctx)
+    sc.set_triangles(tris)
+    sc.build()
+    nodes, glob = sc.bvh_download()
+    assert len(glob) == 0 and nodes.shape[0] == len(tris) - 1
+    depth, proper = _tree_stats(nodes, len(tris))
+    assert proper and depth <= 56, (proper, depth)
+    gid, gt, _ = ctx.trace_batch(sc, rays)
+    oid, ot = oracle.trace_triangles(tris, rays)[:2]
+    same = gid == oid                              # lowest id wins exact ties on both sides; edge grazes aside
+    assert same.mean() > 0.9995, same.mean()
+    hit = same & (oid >= 0)
+    assert hit.mean() > 0.2 and np.all(np.abs(gt[hit] - ot[hit]) <= 1e-5 * ot[hit])
+    print(f"{builder}: depth {depth}")
+
+
 def test_host_trace_pipeline_equals_device_path(ctx):
     """pt_trace_batch (host rays in, host ids/t out): the chunked three-stream pipeline (staging threads, H2D | sort +
     trace + unpack | D2H) returns exactly what one pt_trace_batch_device call over the whole batch returns — several
