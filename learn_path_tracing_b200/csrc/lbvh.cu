@@ -181,13 +181,13 @@ __device__ __forceinline__ float merged_area(float4 al, float4 ah, float4 bl, fl
 // is among them (a run of identical boxes — duplicated faces — then pairs up and halves every round instead of merging
 // once per round), else to the lowest index.  With that rule the lexicographically first of the globally closest pairs
 // is always mutual, so every round merges at least once.
-__global__ void k_ploc_nn(int c, const float4* __restrict__ lo, const float4* __restrict__ hi, int* __restrict__ nn) {
+__global__ void k_ploc_nn(int c, int radius, const float4* __restrict__ lo, const float4* __restrict__ hi, int* __restrict__ nn) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c) return;
     const float4 al = lo[i], ah = hi[i];
     float best = INFINITY;
     int bj = -1;
-    const int j0 = max(0, i - PT_PLOC_RADIUS), j1 = min(c - 1, i + PT_PLOC_RADIUS);
+    const int j0 = max(0, i - radius), j1 = min(c - 1, i + radius);
     for (int j = j0; j <= j1; ++j) {
         if (j == i) continue;
         const float a = merged_area(al, ah, lo[j], hi[j]);
@@ -331,6 +331,8 @@ int pt_lbvh_build(PtContext* ctx, const float4* d_prim_aabb, const int* d_local_
     PT_CUDA(sc.alloc(&d_cost, 2));
 
     // one hierarchy (Karras or PLOC) + refit into `out`; its SAH cost (sum of all child-box areas) into d_cost[slot]
+    const char* renv = getenv("PT_PLOC_RADIUS");  // search radius in Morton order (A/B runs)
+    const int radius = renv && atoi(renv) > 0 ? atoi(renv) : PT_PLOC_RADIUS;
     auto build = [&](bool ploc, float4* out, int slot) -> int {
         PT_CUDA(cudaMemsetAsync(flags, 0, (size_t)(n - 1) * sizeof(int), st));
         if (ploc) {
@@ -353,7 +355,7 @@ int pt_lbvh_build(PtContext* ctx, const float4* d_prim_aabb, const int* d_local_
             int c = (int)n, cur = 0, rounds = 0;
             while (c > 1) {
                 const unsigned g = (unsigned)((c + B - 1) / B);
-                k_ploc_nn<<<g, B, 0, st>>>(c, lo[cur], hi[cur], nn);
+                k_ploc_nn<<<g, B, 0, st>>>(c, radius, lo[cur], hi[cur], nn);
                 k_ploc_merge<<<g, B, 0, st>>>(c, n, nn, ref[cur], lo[cur], hi[cur], keep, ctl, children, parent);
                 PT_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, keep, pos, c, st));
                 k_ploc_compact<<<g, B, 0, st>>>(c, keep, pos, ref[cur], lo[cur], hi[cur], ref[cur ^ 1], lo[cur ^ 1], hi[cur ^ 1], ctl + 1);
