@@ -133,7 +133,7 @@ __device__ __forceinline__ void child_box(int c, const int* __restrict__ sorted_
 
 __global__ void k_refit_emit(long long n, const int2* __restrict__ children, const int* __restrict__ parent,
                              const int* __restrict__ sorted_prim, const float4* __restrict__ aabb, float4* node_box,
-                             int* flags, float4* __restrict__ nodes) {
+                             int* flags, float4* __restrict__ nodes, int* subtree /* inner nodes per subtree, or NULL */) {
     const long long leaf = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (leaf >= n) return;
     int cur = parent[(n - 1) + leaf];
@@ -153,6 +153,7 @@ __global__ void k_refit_emit(long long n, const int2* __restrict__ children, con
         o[3] = make_float4(__int_as_float(r0), __int_as_float(r1), 0.0f, 0.0f);
         __stcg(&node_box[2 * (size_t)cur], make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.0f));
         __stcg(&node_box[2 * (size_t)cur + 1], make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.0f));
+        if (subtree) __stcg(&subtree[cur], 1 + (ch.x >= 0 ? __ldcg(&subtree[ch.x]) : 0) + (ch.y >= 0 ? __ldcg(&subtree[ch.y]) : 0));
         __threadfence();
         cur = parent[cur];
     }
@@ -229,6 +230,34 @@ __global__ void k_ploc_compact(int c, const int* __restrict__ keep, const int* _
         ref2[q] = ref[i]; lo2[q] = lo[i]; hi2[q] = hi[i];
     }
     if (i == c - 1) *count = pos[i] + keep[i];
+}
+
+// Depth-first (pre-order) renumbering of a tree whose nodes were numbered in creation order (PLOC: by merge round, so
+// a parent sits far from its children): the position of a node is the number of inner nodes visited before it, read
+// off the path to the root from the subtree sizes.  Afterwards a subtree is one contiguous run of nodes and the first
+// child follows its parent directly — half of the descents stay in the 128-byte line they came from.
+__global__ void k_dfs_index(long long n_nodes, const int2* __restrict__ children, const int* __restrict__ parent,
+                            const int* __restrict__ subtree, int* __restrict__ newid) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    int idx = 0, c = (int)i, p;
+    while ((p = parent[c]) >= 0) {
+        const int2 ch = children[p];
+        idx += 1 + ((ch.y == c && ch.x >= 0) ? subtree[ch.x] : 0);
+        c = p;
+    }
+    newid[i] = idx;
+}
+__global__ void k_relayout(long long n_nodes, const float4* __restrict__ in, const int* __restrict__ newid, float4* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const float4 a = in[4 * i], b = in[4 * i + 1], c = in[4 * i + 2];
+    float4 k = in[4 * i + 3];
+    const int r0 = __float_as_int(k.x), r1 = __float_as_int(k.y);
+    if (r0 >= 0) k.x = __int_as_float(newid[r0]);
+    if (r1 >= 0) k.y = __int_as_float(newid[r1]);
+    float4* o = out + 4 * (size_t)newid[i];
+    o[0] = a; o[1] = b; o[2] = c; o[3] = k;
 }
 
 // SAH cost of an emitted tree up to constants: the sum of the surface areas of every child box
@@ -331,6 +360,10 @@ int pt_lbvh_build(PtContext* ctx, const float4* d_prim_aabb, const int* d_local_
     PT_CUDA(sc.alloc(&d_cost, 2));
 
     // one hierarchy (Karras or PLOC) + refit into `out`; its SAH cost (sum of all child-box areas) into d_cost[slot]
+    int *subtree = nullptr, *newid = nullptr;
+    float4* nodes_tmp = nullptr;
+    const char* denv = getenv("PT_PLOC_DFS");  // "0": keep PLOC's creation-order numbering (A/B runs)
+    const bool dfs = !(denv && denv[0] == '0');
     const char* renv = getenv("PT_PLOC_RADIUS");  // search radius in Morton order (A/B runs)
     const int radius = renv && atoi(renv) > 0 ? atoi(renv) : PT_PLOC_RADIUS;
     auto build = [&](bool ploc, float4* out, int slot) -> int {
@@ -374,7 +407,19 @@ int pt_lbvh_build(PtContext* ctx, const float4* d_prim_aabb, const int* d_local_
         } else {
             k_hierarchy<<<(unsigned)((n - 1 + B - 1) / B), B, 0, st>>>(kb.Current(), n, children, parent);
         }
-        k_refit_emit<<<gridN, B, 0, st>>>(n, children, parent, vb.Current(), d_prim_aabb, node_box, flags, out);
+        if (ploc && dfs) {  // PLOC numbers nodes by merge round: renumber depth-first (see k_dfs_index)
+            if (!subtree) {
+                PT_CUDA(sc.alloc(&subtree, (size_t)(n - 1)));
+                PT_CUDA(sc.alloc(&newid, (size_t)(n - 1)));
+                PT_CUDA(sc.alloc(&nodes_tmp, (size_t)(n - 1) * 4));
+            }
+            const unsigned gi = (unsigned)((n - 1 + B - 1) / B);
+            k_refit_emit<<<gridN, B, 0, st>>>(n, children, parent, vb.Current(), d_prim_aabb, node_box, flags, nodes_tmp, subtree);
+            k_dfs_index<<<gi, B, 0, st>>>(n - 1, children, parent, subtree, newid);
+            k_relayout<<<gi, B, 0, st>>>(n - 1, nodes_tmp, newid, out);
+        } else {
+            k_refit_emit<<<gridN, B, 0, st>>>(n, children, parent, vb.Current(), d_prim_aabb, node_box, flags, out, nullptr);
+        }
         k_sah_cost<<<(unsigned)((n - 1 + B - 1) / B), B, 0, st>>>(out, n - 1, d_cost + slot);
         PT_CUDA(cudaStreamSynchronize(st));
         PT_CUDA(cudaGetLastError());
