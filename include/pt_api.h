@@ -108,7 +108,8 @@ typedef struct PtRenderParams {
     int32_t reserved[6];    /* [0] wavefront mode: 0 auto (= 3), 1 split (k_extend +
                                    k_shade per bounce), 2 fused K-step (k_paths), 3 persistent ballot-scheduled (k_paths_persist),
                                    4 experimental: persistent + block-local shading queues (k_paths_queue, slower)
-                               [1] fused mode: ray segments per path slot per launch (0 = default 32)
+                                   5 experimental: persistent + two lane-private path records per lane (k_paths_dual, slower)
+                               [1] fused mode: ray segments per path slot per launch (0 = default 32); mode 5: blocks per SM (3 or 4)
                                [2] persistent mode: finished lanes that trigger shading + refill (0 = default 22)
                                [3] persistent mode: waiting lanes that trigger a service (leaf tests) (0 = default 8)  */
 } PtRenderParams; /* 64 bytes */
@@ -171,7 +172,11 @@ int pt_scene_set_texture_atlas(PtScene* s, const uint8_t* texels, int W, int H, 
  * (backbround_color, 10_final/__main__.py:58-62).                                               */
 int pt_scene_set_environment(PtScene* s, const float* rgb, int W, int H, const int32_t* area);
 
-/* GPU LBVH build (Morton codes -> radix sort -> Karras hierarchy -> bottom-up refit). */
+/* GPU BVH build, replaces the host-Python SAH builders (15_module.py:608-634, 716-754): Morton codes -> radix sort ->
+ * hierarchy -> bottom-up refit.  Trees of up to 2^20 primitives are built with BOTH hierarchies over that one sort —
+ * Karras 2012 and PLOC (depth-first renumbered) — and the one with the lower SAH cost is kept; larger trees use the
+ * Karras hierarchy.  Developer knobs (environment, A/B runs only): PT_BUILDER=lbvh|ploc forces one,
+ * PT_PLOC_RADIUS, PT_PLOC_DFS=0, PT_BUILD_VERBOSE=1 prints both SAH costs.                                          */
 int pt_scene_build(PtScene* s);
 
 /* introspection for tests / the oracle: BVH2 nodes as float[n_nodes][16]
