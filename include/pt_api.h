@@ -174,8 +174,9 @@ int pt_scene_set_environment(PtScene* s, const float* rgb, int W, int H, const i
 
 /* GPU BVH build, replaces the host-Python SAH builders (15_module.py:608-634, 716-754): Morton codes -> radix sort ->
  * hierarchy -> bottom-up refit.  Trees of up to 2^20 primitives are built with BOTH hierarchies over that one sort —
- * Karras 2012 and PLOC (depth-first renumbered) — and the one with the lower SAH cost is kept; larger trees use the
- * Karras hierarchy.  Developer knobs (environment, A/B runs only): PT_BUILDER=lbvh|ploc forces one,
+ * Karras 2012 and PLOC (depth-first renumbered) — trees of up to 4096 primitives also by a host full-sweep SAH, and the
+ * candidate with the lowest SAH cost (and at most 60 levels) is kept; larger trees use the Karras hierarchy.
+ * Developer knobs (environment, A/B runs only): PT_BUILDER=lbvh|ploc|sah forces one,
  * PT_PLOC_RADIUS, PT_PLOC_DFS=0, PT_BUILD_VERBOSE=1 prints both SAH costs.                                          */
 int pt_scene_build(PtScene* s);
 

@@ -17,10 +17,15 @@
 #include <cub/device/device_scan.cuh>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <utility>
+#include <vector>
 
 #include "pt_internal.h"
 
+#define PT_MAX_TREE_DEPTH 60   // candidates deeper than this are discarded (traversal stack: 64 entries); the Karras tree
+                               // is bounded by its 63 key bits + log2 of the longest run of equal codes
+#define PT_HOST_SAH_MAX 4096   // up to here a full-sweep SAH tree from the host competes as well (see host_sah_rec)
 #define PT_PLOC_MAX (1 << 20)  // larger trees keep the Karras hierarchy (one pass instead of ~30 rounds over all clusters)
 
 namespace {
@@ -237,16 +242,18 @@ __global__ void k_ploc_compact(int c, const int* __restrict__ keep, const int* _
 // off the path to the root from the subtree sizes.  Afterwards a subtree is one contiguous run of nodes and the first
 // child follows its parent directly — half of the descents stay in the 128-byte line they came from.
 __global__ void k_dfs_index(long long n_nodes, const int2* __restrict__ children, const int* __restrict__ parent,
-                            const int* __restrict__ subtree, int* __restrict__ newid) {
+                            const int* __restrict__ subtree, int* __restrict__ newid, int* __restrict__ max_depth) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
-    int idx = 0, c = (int)i, p;
+    int idx = 0, c = (int)i, p, depth = 2;  // this node + the leaves below it
     while ((p = parent[c]) >= 0) {
         const int2 ch = children[p];
         idx += 1 + ((ch.y == c && ch.x >= 0) ? subtree[ch.x] : 0);
         c = p;
+        ++depth;
     }
     newid[i] = idx;
+    if (depth > PT_MAX_TREE_DEPTH) atomicMax(max_depth, depth);
 }
 __global__ void k_relayout(long long n_nodes, const float4* __restrict__ in, const int* __restrict__ newid, float4* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -299,6 +306,61 @@ __global__ void k_quantize_nodes(const float4* __restrict__ nodes, long long n, 
     const unsigned M1x = q_up(c.y, lo.x, sc.x), M1y = q_up(c.z, lo.y, sc.y), M1z = q_up(c.w, lo.z, sc.z);
     out[2 * i] = make_uint4(m0x | m0y << 16, m0z | M0x << 16, M0y | M0z << 16, m1x | m1y << 16);
     out[2 * i + 1] = make_uint4(m1z | M1x << 16, M1y | M1z << 16, __float_as_uint(k.x), __float_as_uint(k.y));
+}
+
+// ---- host full-sweep SAH for tiny trees ------------------------------------------------------------
+// A few hundred primitives (the RTIOW sphere field: 485) are not worth a device builder's launches, and neither Morton
+// hierarchy is good on them (CPU prototype, tools/tree_quality_proto.py: full-sweep SAH cost 4561 against 5162 Karras /
+// 5378 PLOC, 3-10 % fewer node visits).  Top-down, every split evaluated on all three axes, one primitive per leaf,
+// nodes emitted depth-first (root = 0) in the layout k_refit_emit writes.  O(n log^2 n): ~0.2 ms for 485 primitives.
+struct HostBox { float lo[3], hi[3]; };
+static inline float hb_area(const HostBox& b) {
+    const float x = b.hi[0] - b.lo[0], y = b.hi[1] - b.lo[1], z = b.hi[2] - b.lo[2];
+    return x * y + y * z + z * x;
+}
+static inline void hb_grow(HostBox& a, const HostBox& b) {
+    for (int c = 0; c < 3; ++c) { a.lo[c] = std::min(a.lo[c], b.lo[c]); a.hi[c] = std::max(a.hi[c], b.hi[c]); }
+}
+// builds the subtree over idx[begin, end) (indices into box/prim); returns its child reference, its box in *out
+static int host_sah_rec(std::vector<int>& idx, int begin, int end, const std::vector<HostBox>& box, const std::vector<int>& prim,
+                        std::vector<float>& nodes, std::vector<float>& tmp_area, HostBox* out, int depth, int* max_depth) {
+    const int cnt = end - begin;
+    if (depth > *max_depth) *max_depth = depth;
+    if (cnt == 1) { *out = box[idx[begin]]; return ~prim[idx[begin]]; }
+    int best_axis = 0, best_k = 1;
+    float best_cost = INFINITY;
+    std::vector<int> order(idx.begin() + begin, idx.begin() + end), best_order;
+    for (int ax = 0; ax < 3; ++ax) {
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            return box[a].lo[ax] + box[a].hi[ax] < box[b].lo[ax] + box[b].hi[ax];
+        });
+        HostBox acc = box[order[cnt - 1]];
+        tmp_area[cnt - 1] = hb_area(acc);
+        for (int k = cnt - 2; k >= 1; --k) { hb_grow(acc, box[order[k]]); tmp_area[k] = hb_area(acc); }  // area of [k, cnt)
+        acc = box[order[0]];
+        for (int k = 1; k < cnt; ++k) {   // split: [0, k) | [k, cnt)
+            const float cost = hb_area(acc) * (float)k + tmp_area[k] * (float)(cnt - k);
+            // equal costs (identical boxes): the more balanced split, or the tree degenerates into a chain
+            if (cost < best_cost || (cost == best_cost && abs(2 * k - cnt) < abs(2 * best_k - cnt))) {
+                best_cost = cost; best_axis = ax; best_k = k;
+            }
+            hb_grow(acc, box[order[k]]);
+        }
+        if (best_axis == ax) best_order = order;
+    }
+    std::copy(best_order.begin(), best_order.end(), idx.begin() + begin);
+    const size_t me = nodes.size() / 16;
+    nodes.resize(nodes.size() + 16, 0.0f);
+    HostBox b0, b1;
+    const int r0 = host_sah_rec(idx, begin, begin + best_k, box, prim, nodes, tmp_area, &b0, depth + 1, max_depth);
+    const int r1 = host_sah_rec(idx, begin + best_k, end, box, prim, nodes, tmp_area, &b1, depth + 1, max_depth);
+    float* o = &nodes[16 * me];
+    for (int c = 0; c < 3; ++c) { o[c] = b0.lo[c]; o[3 + c] = b0.hi[c]; o[6 + c] = b1.lo[c]; o[9 + c] = b1.hi[c]; }
+    memcpy(&o[12], &r0, 4);
+    memcpy(&o[13], &r1, 4);
+    *out = b0;
+    hb_grow(*out, b1);
+    return (int)me;
 }
 
 struct Scratch {
@@ -358,6 +420,9 @@ int pt_lbvh_build(PtContext* ctx, const float4* d_prim_aabb, const int* d_local_
     size_t scan_bytes = 0;
     double* d_cost = nullptr;
     PT_CUDA(sc.alloc(&d_cost, 2));
+    int* d_depth = nullptr;  // deepest PLOC leaf when it exceeds PT_MAX_TREE_DEPTH, else 0
+    PT_CUDA(sc.alloc(&d_depth, 1));
+    PT_CUDA(cudaMemsetAsync(d_depth, 0, sizeof(int), st));
 
     // one hierarchy (Karras or PLOC) + refit into `out`; its SAH cost (sum of all child-box areas) into d_cost[slot]
     int *subtree = nullptr, *newid = nullptr;
@@ -415,7 +480,7 @@ int pt_lbvh_build(PtContext* ctx, const float4* d_prim_aabb, const int* d_local_
             }
             const unsigned gi = (unsigned)((n - 1 + B - 1) / B);
             k_refit_emit<<<gridN, B, 0, st>>>(n, children, parent, vb.Current(), d_prim_aabb, node_box, flags, nodes_tmp, subtree);
-            k_dfs_index<<<gi, B, 0, st>>>(n - 1, children, parent, subtree, newid);
+            k_dfs_index<<<gi, B, 0, st>>>(n - 1, children, parent, subtree, newid, d_depth);
             k_relayout<<<gi, B, 0, st>>>(n - 1, nodes_tmp, newid, out);
         } else {
             k_refit_emit<<<gridN, B, 0, st>>>(n, children, parent, vb.Current(), d_prim_aabb, node_box, flags, out, nullptr);
@@ -433,7 +498,45 @@ int pt_lbvh_build(PtContext* ctx, const float4* d_prim_aabb, const int* d_local_
     const bool force = env && env[0];
     PT_CUDA(cudaMemsetAsync(d_cost, 0, 2 * sizeof(double), st));
     int rcb;
-    if (force || n > PT_PLOC_MAX) {
+    // host full-sweep SAH (tiny trees): boxes down, nodes up, cost through the same kernel
+    auto host_sah = [&](float4* out, double* cost_out) -> int {
+        std::vector<int> prim((size_t)n);
+        PT_CUDA(cudaMemcpy(prim.data(), d_local_ids, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+        std::vector<HostBox> box((size_t)n);
+        {
+            int max_p = 0;
+            for (int p : prim) max_p = std::max(max_p, p);
+            std::vector<float4> all((size_t)(max_p + 1) * 2);
+            PT_CUDA(cudaMemcpy(all.data(), d_prim_aabb, all.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+            for (int64_t k = 0; k < n; ++k) {
+                const float4 a = all[2 * (size_t)prim[k]], b = all[2 * (size_t)prim[k] + 1];
+                box[k].lo[0] = a.x; box[k].lo[1] = a.y; box[k].lo[2] = a.z;
+                box[k].hi[0] = b.x; box[k].hi[1] = b.y; box[k].hi[2] = b.z;
+            }
+        }
+        std::vector<int> idx((size_t)n);
+        for (int64_t k = 0; k < n; ++k) idx[k] = (int)k;
+        std::vector<float> hn, tmp_area((size_t)n);
+        hn.reserve((size_t)(n - 1) * 16);
+        HostBox root_box;
+        int depth = 0;
+        host_sah_rec(idx, 0, (int)n, box, prim, hn, tmp_area, &root_box, 0, &depth);
+        PT_REQUIRE((int64_t)hn.size() == (n - 1) * 16, "host SAH emitted a wrong node count");
+        if (depth > PT_MAX_TREE_DEPTH) {  // would not fit the traversal stack: not a candidate
+            *cost_out = INFINITY;
+            return PT_OK;
+        }
+        PT_CUDA(cudaMemcpy(out, hn.data(), hn.size() * sizeof(float), cudaMemcpyHostToDevice));
+        PT_CUDA(cudaMemsetAsync(d_cost + 1, 0, sizeof(double), st));
+        k_sah_cost<<<(unsigned)((n - 1 + B - 1) / B), B, 0, st>>>(out, n - 1, d_cost + 1);
+        PT_CUDA(cudaMemcpyAsync(cost_out, d_cost + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
+        PT_CUDA(cudaStreamSynchronize(st));
+        return PT_OK;
+    };
+    if (force && env[0] == 's') {
+        double c = 0.0;
+        rcb = host_sah(nodes, &c);
+    } else if (force || n > PT_PLOC_MAX) {
         rcb = build(force && env[0] == 'p', nodes, 0);
     } else {
         float4* nodes2 = nullptr;
@@ -443,8 +546,17 @@ int pt_lbvh_build(PtContext* ctx, const float4* d_prim_aabb, const int* d_local_
         if (rcb == PT_OK) rcb = build(true, nodes2, 1);
         double cost[2] = {0.0, 0.0};
         if (rcb == PT_OK && cudaMemcpy(cost, d_cost, sizeof cost, cudaMemcpyDeviceToHost) != cudaSuccess) rcb = PT_ERR_CUDA;
-        if (getenv("PT_BUILD_VERBOSE")) fprintf(stderr, "[libb200pt] %lld prims: SAH cost lbvh %.6g, ploc %.6g\n", (long long)n, cost[0], cost[1]);
-        if (rcb == PT_OK && cost[1] < cost[0]) std::swap(nodes, nodes2);
+        int ploc_depth = 0;
+        if (rcb == PT_OK && cudaMemcpy(&ploc_depth, d_depth, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) rcb = PT_ERR_CUDA;
+        if (ploc_depth > PT_MAX_TREE_DEPTH) cost[1] = INFINITY;  // would not fit the traversal stack: not a candidate
+        if (rcb == PT_OK && cost[1] < cost[0]) { std::swap(nodes, nodes2); cost[0] = cost[1]; }
+        double cost_sah = -1.0;
+        if (rcb == PT_OK && n <= PT_HOST_SAH_MAX) {  // tiny tree: a third candidate from the host (nodes2 is free again)
+            rcb = host_sah(nodes2, &cost_sah);
+            if (rcb == PT_OK && cost_sah < cost[0]) std::swap(nodes, nodes2);
+        }
+        if (getenv("PT_BUILD_VERBOSE"))
+            fprintf(stderr, "[libb200pt] %lld prims: SAH cost best of lbvh/ploc %.6g (ploc %.6g), host sweep %.6g\n", (long long)n, cost[0], cost[1], cost_sah);
         cudaFree(nodes2);
     }
     if (rcb) {

@@ -302,9 +302,9 @@ def _tree_stats(nodes, n_prims):
     return int(depth.max()) + 1, len(order) == nodes.shape[0] and bool((seen == 1).all())
 
 
-@pytest.mark.parametrize("builder", ["ploc", "lbvh", ""])   # "": both are built, the lower SAH cost is kept
+@pytest.mark.parametrize("builder", ["ploc", "lbvh", "sah", ""])   # "": all candidates are built, the lowest SAH cost is kept
 def test_tree_builders_are_valid_and_equivalent(ctx, oracle, builder, monkeypatch):
-    """Both hierarchy builders (Karras LBVH, PLOC over the same Morton order) emit a proper binary tree over every
+    """The hierarchy builders (Karras LBVH, PLOC over the same Morton order, the host full-sweep SAH of tiny trees) emit a proper binary tree over every
     primitive, shallow enough for the 64-entry traversal stack — also with thousands of exactly duplicated triangles
     (the Genshin models double their two-sided faces) — and the closest hits do not depend on which one built it."""
     monkeypatch.setenv("PT_BUILDER", builder)
