@@ -67,6 +67,8 @@ extern "C" {
                                    entry-point/direction Morton order; results always land in batch order) */
 #define PT_FLAG_TRACE_SIMPLE 16 /* one ray per thread (k_trace) instead of the persistent while-while warps */
 #define PT_FLAG_NO_QNODES 32    /* walk the 64-byte float nodes even when the tree has the 32-byte quantised copy */
+#define PT_FLAG_TRACE_WIDE 128  /* EXPERIMENTAL: walk the 4-wide copy of the tree (scene built with PT_WIDE=1 in the
+                                   environment; csrc/bvh4.h); same hit records, fewer steps                        */
 /* bits 8-13 of the trace flags: lanes that must wait before a warp services them (0 = default 8);
    bits 14-19: finished lanes that trigger result write-back + refill (0 = default 8) */
 

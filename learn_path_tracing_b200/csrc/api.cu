@@ -1,11 +1,13 @@
 // api.cu — handles, scene upload/build and the host-buffer entry points of include/pt_api.h.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 #include <thread>
 
+#include "bvh4.h"
 #include "pt_internal.h"
 
 #define PT_QNODES_MIN (1 << 18)  // trees from 256 Ki nodes (16 MiB of 64-byte nodes) on get the quantised copy
@@ -151,12 +153,16 @@ extern "C" int pt_scene_create(PtContext* ctx, PtScene** out) {
 }
 
 static void free_device(PtScene* s) {
-    void* ptrs[] = {s->d_sph_cr, s->d_sph_aux, s->d_sph_mat, s->d_tri_geo, s->d_tri_shade, s->d_nodes, s->d_global, s->d_qnodes};
+    void* ptrs[] = {s->d_sph_cr, s->d_sph_aux, s->d_sph_mat, s->d_tri_geo, s->d_tri_shade, s->d_nodes, s->d_global, s->d_qnodes,
+                    s->d_wnodes};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     s->d_sph_cr = s->d_sph_aux = s->d_sph_mat = s->d_tri_geo = s->d_tri_shade = s->d_nodes = nullptr;
     s->d_global = nullptr;
     s->d_qnodes = nullptr;
+    s->d_wnodes = nullptr;
+    s->n_wnodes = 0;
+    s->view.wnodes = nullptr;
     s->built = false;
 }
 
@@ -589,6 +595,21 @@ extern "C" int pt_scene_build(PtScene* s) {
         if (rcq) return rcq;
         s->view.qnodes = s->d_qnodes;
         for (int c = 0; c < 3; ++c) { s->view.qlo[c] = s->bounds_lo[c]; s->view.qscale[c] = scale[c]; }
+    }
+    // EXPERIMENTAL (PT_WIDE=1): 4-wide copy of the tree, collapsed on the host (bvh4.h), for k_trace_persist<.., WIDE>
+    s->view.wnodes = nullptr;
+    {
+        const char* wenv = getenv("PT_WIDE");
+        if (wenv && wenv[0] == '1' && root != PT_NO_BVH && s->n_nodes > 0) {
+            std::vector<float> h2((size_t)s->n_nodes * 16);
+            PT_CUDA(cudaMemcpy(h2.data(), s->d_nodes, h2.size() * sizeof(float), cudaMemcpyDeviceToHost));
+            const std::vector<float> w = bvh4::collapse(h2.data(), s->n_nodes);
+            PT_REQUIRE(!w.empty(), "bvh4 collapse produced no nodes");
+            PT_CUDA(cudaMalloc(&s->d_wnodes, w.size() * sizeof(float)));
+            PT_CUDA(cudaMemcpy(s->d_wnodes, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+            s->n_wnodes = (int64_t)(w.size() / BVH4_NODE_FLOATS);
+            s->view.wnodes = s->d_wnodes;
+        }
     }
     SceneView& v = s->view;
     v.sph_cr = s->d_sph_cr; v.sph_aux = s->d_sph_aux; v.sph_mat = s->d_sph_mat;

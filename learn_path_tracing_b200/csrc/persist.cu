@@ -175,12 +175,14 @@ k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* _
 // batch order).  Result i is written to hits[i] of the ORIGINAL batch order.
 // 6 blocks of 256 threads per SM (40 registers, a few spilled words): ncu shows this kernel latency-bound (long
 // scoreboard 8.7 warps per issue at 4 blocks); measured 1.34 / 1.54 / 1.62 Grays/s at 4 / 5 / 6 blocks, 0.93 at 7+
-template <bool COUNT, bool QNODES>
-__global__ void __launch_bounds__(PT_BLOCK, 6)
+// WIDE (experimental, opt-in): walks the 4-wide copy of the tree (extend.cuh:node_step4) with a 128-entry
+// stack at 4 blocks/SM (three 256-bit loads per step want the registers).
+template <bool COUNT, bool QNODES, bool WIDE = false>
+__global__ void __launch_bounds__(PT_BLOCK, WIDE ? 4 : 6)
 k_trace_persist(const SceneView sv, const float4* __restrict__ rays, const unsigned* __restrict__ order,
                 float4* __restrict__ hits, long long n, unsigned long long* __restrict__ counters, int serve_min,
                 int fetch_min) {
-    int stack[PT_STACK];
+    int stack[WIDE ? PT_STACK_WIDE : PT_STACK];
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt = (1u << lane) - 1u;
     float3 o = f3(0, 0, 0), d = f3(0, 0, 1);
@@ -198,10 +200,11 @@ k_trace_persist(const SceneView sv, const float4* __restrict__ rays, const unsig
         const int n_inner = __popc(__ballot_sync(0xffffffffu, inner));
         if (n_inner > walk_min) {
             if (inner) {
-                if (QNODES) node_step_q<COUNT>(sv, T, stack, tc);
+                if (WIDE) node_step4<COUNT>(sv, T, stack, tc);
+                else if (QNODES) node_step_q<COUNT>(sv, T, stack, tc);
                 else node_step<COUNT>(sv, T, stack, tc);
                 // a second step on the same vote (the vote costs about a quarter of a step)
-                if (n_inner > walk_min + 4 && PT_IS_INNER(T.cur)) {
+                if (!WIDE && n_inner > walk_min + 4 && PT_IS_INNER(T.cur)) {
                     if (QNODES) node_step_q<COUNT>(sv, T, stack, tc);
                     else node_step<COUNT>(sv, T, stack, tc);
                 }
@@ -318,7 +321,7 @@ static int resident_blocks(PtContext* ctx, K kernel, int* out) {
 }
 
 int pt_trace_persist(PtContext* ctx, const PtScene* s, const float4* rays, long long n, float4* hits, bool count,
-                     bool sort, bool use_qnodes, int serve_min, int fetch_min, cudaEvent_t ev_sorted) {
+                     bool sort, bool use_qnodes, int serve_min, int fetch_min, cudaEvent_t ev_sorted, bool wide) {
     cudaStream_t st = ctx->stream;
     const unsigned* order = nullptr;
     if (sort && n > 1) {
@@ -341,6 +344,17 @@ int pt_trace_persist(PtContext* ctx, const PtScene* s, const float4* rays, long 
         order = vb.Current();
     }
     if (ev_sorted) PT_CUDA(cudaEventRecord(ev_sorted, st));
+    if (wide) {  // experimental 4-wide walk (PT_FLAG_TRACE_WIDE): float nodes only
+        int wblocks = 0;
+        int rcw = count ? resident_blocks(ctx, k_trace_persist<true, false, true>, &wblocks) : resident_blocks(ctx, k_trace_persist<false, false, true>, &wblocks);
+        if (rcw) return rcw;
+        const long long wneed = (n + PT_BLOCK - 1) / PT_BLOCK;
+        if (wblocks > wneed) wblocks = (int)wneed;
+        if (count) k_trace_persist<true, false, true><<<wblocks, PT_BLOCK, 0, st>>>(s->view, rays, order, hits, n, ctx->counters, serve_min, fetch_min);
+        else k_trace_persist<false, false, true><<<wblocks, PT_BLOCK, 0, st>>>(s->view, rays, order, hits, n, ctx->counters, serve_min, fetch_min);
+        PT_CUDA(cudaGetLastError());
+        return PT_OK;
+    }
     int blocks = 0, rcb;
     const bool q = s->view.qnodes != nullptr && use_qnodes;
     if (count) rcb = q ? resident_blocks(ctx, k_trace_persist<true, true>, &blocks) : resident_blocks(ctx, k_trace_persist<true, false>, &blocks);

@@ -59,6 +59,9 @@ struct SceneView {
     int inl_transparent[PT_MAX_INLINE];
     float inl_r2[PT_MAX_INLINE];
     float4 inl_cr[PT_MAX_INLINE];
+    // EXPERIMENTAL 4-wide copy of the tree (bvh4.h: 8 float4 per node, root = 0), NULL unless the scene was built with
+    // PT_WIDE=1 in the environment; only k_trace_persist<.., WIDE> reads it (PT_FLAG_TRACE_WIDE)
+    const float4* wnodes;
 };
 
 #define PT_NO_BVH 0x7fffffff
@@ -116,6 +119,8 @@ struct PtScene {
     float4 *d_sph_cr = nullptr, *d_sph_aux = nullptr, *d_sph_mat = nullptr;
     float4 *d_tri_geo = nullptr, *d_tri_shade = nullptr, *d_nodes = nullptr;
     uint4* d_qnodes = nullptr;
+    float4* d_wnodes = nullptr;
+    int64_t n_wnodes = 0;
     int* d_global = nullptr;
     uint2* d_atlas = nullptr;
     int4* d_tex_areas = nullptr;
@@ -163,7 +168,7 @@ struct RenderConsts;
 int pt_render_persist(PtContext* ctx, const PtScene* s, const RenderConsts& rc, bool legacy, bool count, float4* accum,
                       float4* accum_sq, int shade_min, int serve_min);
 int pt_trace_persist(PtContext* ctx, const PtScene* s, const float4* rays, long long n, float4* hits, bool count,
-                     bool sort, bool use_qnodes, int serve_min, int fetch_min, cudaEvent_t ev_sorted);
+                     bool sort, bool use_qnodes, int serve_min, int fetch_min, cudaEvent_t ev_sorted, bool wide = false);
 // dual.cu — persistent kernel with a lane-private parking place per lane (PT_MODE_DUAL)
 int pt_render_dual(PtContext* ctx, const PtScene* s, const RenderConsts& rc, bool legacy, bool count, float4* accum,
                    float4* accum_sq, int shade_min, int serve_min, int blocks_per_sm);

@@ -590,8 +590,10 @@ extern "C" int pt_trace_batch_device(PtContext* ctx, const PtScene* s, const voi
         } else {  // persistent while-while warps over the (sorted) batch
             const bool sort = !(flags & PT_FLAG_NO_SORT) && n >= (1 << 16);
             const int serve_min = (flags >> 8) & 63, fetch_min = (flags >> 14) & 63;
+            const bool wide = (flags & PT_FLAG_TRACE_WIDE) != 0;
+            PT_REQUIRE(!wide || s->view.wnodes, "PT_FLAG_TRACE_WIDE: the scene has no 4-wide tree (build it with PT_WIDE=1 in the environment)");
             int rct = pt_trace_persist(ctx, s, (const float4*)rays_dev, n, (float4*)hits_dev, count, sort, !(flags & PT_FLAG_NO_QNODES),
-                                       serve_min ? serve_min : 8, fetch_min ? fetch_min : 8, stats ? get_event(ctx, 0) : nullptr);
+                                       serve_min ? serve_min : 8, fetch_min ? fetch_min : 8, stats ? get_event(ctx, 0) : nullptr, wide);
             if (rct) return rct;
             persist = true;
         }

@@ -738,6 +738,58 @@ void orc_trace_bvh2(const float* nodes, int64_t n_nodes, const float* tris9, int
     if (counts) { counts[0] = cn; counts[1] = ct; }
 }
 
+/* the same walk over a 4-wide tree (layout: learn_path_tracing_b200/csrc/bvh4.h — minx[4] miny[4] minz[4] maxx[4] maxy[4]
+ * maxz[4] ref[4] pad[4]; ref 0x7fffffff = empty slot): nearest hit child first, the others in slot order, like the device
+ * step.  Checks the collapsed tree: the hits must equal orc_trace_bvh2's on the tree it was collapsed from. */
+void orc_trace_bvh4(const float* wnodes, int64_t n_nodes, const float* tris9, int64_t ntri, const float* rays,
+                    int64_t nrays, int32_t* prim_id, float* t, uint64_t counts[2]) {
+    uint64_t cn = 0, ct = 0;
+    (void)ntri;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : cn, ct)
+    for (int64_t k = 0; k < nrays; ++k) {
+        V3 o = vload(rays + 8 * k), d = vload(rays + 8 * k + 4);
+        V3 inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        float bt = INFINITY, w[3];
+        int id = -1;
+        int32_t stack[256];
+        int sp = 0;
+        if (n_nodes > 0) stack[sp++] = 0;
+        while (sp > 0) {
+            int32_t cur = stack[--sp];
+            if (cur < 0) { /* leaf */
+                int f = ~cur;
+                const float* T = tris9 + 9 * (size_t)f;
+                ct++;
+                float tt = triangle_hit_t(vload(T), vload(T + 3), vload(T + 6), o, d, w);
+                if (tt > ORC_EPS && (tt < bt || (tt == bt && f < id))) { bt = tt; id = f; }
+                continue;
+            }
+            cn++;
+            const float* N = wnodes + 32 * (size_t)cur;
+            int32_t ref[4];
+            memcpy(ref, N + 24, 16);
+            float tn[4];
+            int hit[4], near = -1;
+            for (int c = 0; c < 4; ++c) {
+                float ax = (N[c] - o.x) * inv.x, bx = (N[12 + c] - o.x) * inv.x;
+                float ay = (N[4 + c] - o.y) * inv.y, by = (N[16 + c] - o.y) * inv.y;
+                float az = (N[8 + c] - o.z) * inv.z, bz = (N[20 + c] - o.z) * inv.z;
+                float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+                float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+                hit[c] = ref[c] != 0x7fffffff && t1 * 1.00001f + 1e-6f >= t0 && t0 * 0.99999f - 1e-6f <= bt;
+                tn[c] = t0;
+                if (hit[c] && (near < 0 || t0 < tn[near])) near = c;
+            }
+            for (int c = 3; c >= 0; --c)
+                if (hit[c] && c != near) stack[sp++] = ref[c];
+            if (near >= 0) stack[sp++] = ref[near];
+        }
+        prim_id[k] = id;
+        t[k] = id >= 0 ? bt : -1.0f;
+    }
+    if (counts) { counts[0] = cn; counts[1] = ct; }
+}
+
 /* reference triangle test for given (ray, triangle) pairs: t (or -1) and the smallest barycentric */
 void orc_triangle_eval(const float* tris9, const int32_t* ids, const float* rays, int64_t nrays, float* t,
                        float* wmin) {

@@ -85,6 +85,8 @@ void orc_trace_triangles(const float* tris, int64_t ntri, const float* rays, int
 
 /* ordered, t-pruned traversal of a BVH2 in the pt_scene_bvh_download layout with the Moller-Trumbore
  * test over tris12[n][12]; counts (optional) = {nodes visited, triangles tested} totals. */
+void orc_trace_bvh4(const float* wnodes, int64_t n_nodes, const float* tris9, int64_t ntri, const float* rays,
+                    int64_t nrays, int32_t* prim_id, float* t, uint64_t counts[2]);
 void orc_trace_bvh2(const float* nodes, int64_t n_nodes, const float* tris12, int64_t ntri, const float* rays,
                     int64_t nrays, int32_t* prim_id, float* t, uint64_t counts[2]);
 

@@ -113,6 +113,37 @@ def trace_bvh2(nodes16, tris9, rays):
     return ids, t, (int(counts[0]), int(counts[1]))
 
 
+def trace_bvh4(wnodes32, tris9, rays):
+    """Walk of a 4-wide tree (csrc/bvh4.h layout) with the reference triangle test -> (ids, t, (nodes, tests))."""
+    nodes = _f32(wnodes32, (-1, 32))
+    tris = _f32(tris9, (-1, 9))
+    rays = _f32(rays, (-1, 8))
+    n = rays.shape[0]
+    ids = np.empty(n, np.int32)
+    t = np.empty(n, np.float32)
+    counts = (C.c_uint64 * 2)()
+    load().orc_trace_bvh4(_p(nodes), C.c_int64(nodes.shape[0]), _p(tris), C.c_int64(tris.shape[0]), _p(rays),
+                          C.c_int64(n), _p(ids), _p(t), counts)
+    return ids, t, (int(counts[0]), int(counts[1]))
+
+
+_bvh4 = None
+
+
+def bvh4_collapse(nodes16):
+    """The PRODUCT's host collapse (csrc/bvh4.h) compiled for the CPU (oracle/bvh4_host.cpp): BVH2 nodes -> wide nodes."""
+    global _bvh4
+    if _bvh4 is None:
+        _bvh4 = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbvh4host.so"))
+        _bvh4.bvh4_collapse_host.restype = C.c_int64
+    nodes = _f32(nodes16, (-1, 16))
+    out = np.zeros((nodes.shape[0] + 1, 32), np.float32)
+    m = _bvh4.bvh4_collapse_host(_p(nodes), C.c_int64(nodes.shape[0]), _p(out), C.c_int64(out.shape[0]))
+    if m < 0:
+        raise RuntimeError("bvh4_collapse_host: output buffer too small")
+    return out[:m].copy()
+
+
 def triangle_eval(tris9, ids, rays):
     tris = _f32(tris9, (-1, 9))
     rays = _f32(rays, (-1, 8))
