@@ -200,6 +200,7 @@ def run_ours(args):
     ev1 = torch.cuda.Event(enable_timing=True)
 
     def step(flags=0):
+        flags |= L.PT_FLAG_WIDE if args.wide else 0
         r.clear()
         st = r.render(scene, cs, spp, depth, model, seed=1, spp_offset=rank * spp, flags=flags, mode=args.mode,
                       pool_capacity=args.pool, segments_per_launch=args.k, shade_min=args.shade_min, serve_min=args.serve_min)
@@ -421,7 +422,8 @@ def run_intersect(args):
         K = args.steps
         nodes_per_ray = st.nodes_visited / n_local
         tris_per_ray = st.prims_tested / n_local
-        bytes_per_ray = 32 + 8 + 64 * nodes_per_ray + 48 * tris_per_ray
+        node_bytes = 128 if (args.trace_flags & L.PT_FLAG_TRACE_WIDE) else 64   # 4-wide nodes are 128 bytes
+        bytes_per_ray = 32 + 8 + node_bytes * nodes_per_ray + 48 * tris_per_ray
         achieved = bytes_per_ray * n_local * K / (t_local * 1e-3) / 1e9
         kname = "k_trace" if (args.trace_flags & L.PT_FLAG_TRACE_SIMPLE) else "k_trace_persist"
         traffic = None
@@ -454,7 +456,7 @@ def run_intersect(args):
                          "traffic_source": traffic["source"] if traffic else None, "peak_kind": peak_kind,
                          "step_ms": {"ray_sort": st_plain.ms_other, "traversal": st_plain.ms_extend, "step": t_local / K},
                          "algorithmic_bytes_per_launch": bytes_per_ray * n_local,
-                         "algorithmic_bytes": f"32 + 8 + 64*{nodes_per_ray:.1f} nodes + 48*{tris_per_ray:.2f} triangles "
+                         "algorithmic_bytes": f"32 + 8 + {node_bytes}*{nodes_per_ray:.1f} nodes + 48*{tris_per_ray:.2f} triangles "
                                               f"= {bytes_per_ray:.0f} B/ray (SURVEY 8d; counts from a counter-instrumented run)",
                          "compulsory_40B_per_ray": {"achieved": 40.0 * n_local * K / (t_local * 1e-3) / 1e9}},
             "cpu_baseline": {"value": n_c / cpu_s / 1e6, "unit": "Mrays/s", "cores": O.num_threads(), "kind": "port",
@@ -480,8 +482,13 @@ def main():
     ap.add_argument("--shade-min", type=int, default=0, help="persistent mode: waiting lanes that trigger shading (0 = default)")
     ap.add_argument("--serve-min", type=int, default=0, help="persistent mode: waiting lanes that trigger a service (0 = default)")
     ap.add_argument("--trace-flags", type=int, default=0, help="intersect workloads: PT_FLAG_* for pt_trace_batch_device")
+    ap.add_argument("--wide", action="store_true",
+                    help="EXPERIMENTAL: build the 4-wide copy of the tree (PT_WIDE=1) and walk it (PT_FLAG_WIDE / PT_FLAG_TRACE_WIDE)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     args = ap.parse_args()
+    if args.wide:
+        os.environ["PT_WIDE"] = "1"          # read by pt_scene_build
+        args.trace_flags |= L.PT_FLAG_TRACE_WIDE
     if args.workload in INTERSECT:
         if args.impl == "reference":
             raise SystemExit("--impl reference: use a render workload (the intersect line carries its own cpu_baseline)")

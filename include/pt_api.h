@@ -69,6 +69,8 @@ extern "C" {
 #define PT_FLAG_NO_QNODES 32    /* walk the 64-byte float nodes even when the tree has the 32-byte quantised copy */
 #define PT_FLAG_TRACE_WIDE 128  /* EXPERIMENTAL: walk the 4-wide copy of the tree (scene built with PT_WIDE=1 in the
                                    environment; csrc/bvh4.h); same hit records, fewer steps                        */
+#define PT_FLAG_WIDE PT_FLAG_TRACE_WIDE /* the same for pt_render (PtRenderParams.flags, persistent mode only): validated in
+                                   pt_trace_batch_device on the B200, NOT YET RUN in the render kernel                 */
 /* bits 8-13 of the trace flags: lanes that must wait before a warp services them (0 = default 8);
    bits 14-19: finished lanes that trigger result write-back + refill (0 = default 8) */
 

@@ -24,6 +24,7 @@ PT_FLAG_ACCUM_SQ = 1
 PT_FLAG_TIMING = 2
 PT_FLAG_COUNTERS = 4
 PT_FLAG_TRACE_WIDE = 128  # experimental 4-wide traversal (scene built with PT_WIDE=1)
+PT_FLAG_WIDE = PT_FLAG_TRACE_WIDE  # the same bit in PtRenderParams.flags (persistent mode; not yet run on a GPU)
 PT_FLAG_PIXEL_GRID = 64  # stages 2-4 camera: lattice rays i/(W-1), j/(H-1), no jitter
 
 PT_MODE_AUTO = 0

@@ -37,11 +37,13 @@
 #define PT_TILE_H 4
 #define PT_UNIT_SAMPLES 16
 
-template <bool LEGACY, bool COUNT>
+// WIDE (experimental, opt-in: PT_WIDE=1 at build time + PT_FLAG_WIDE; NOT YET RUN ON A GPU in this kernel — the step
+// itself, extend.cuh:node_step4, is validated in k_trace_persist): the node phase walks the 4-wide copy of the tree.
+template <bool LEGACY, bool COUNT, bool WIDE = false>
 __global__ void __launch_bounds__(PT_BLOCK, 4)
 k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* __restrict__ counters,
                 float4* __restrict__ accum, float4* __restrict__ accum_sq, int shade_min, int serve_min) {
-    int stack[PT_STACK];
+    int stack[WIDE ? PT_STACK_WIDE : PT_STACK];
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt = (1u << lane) - 1u;
     const unsigned tiles_x = ((unsigned)rc.W + PT_TILE_W - 1) / PT_TILE_W, tiles_y = ((unsigned)rc.H + PT_TILE_H - 1) / PT_TILE_H;
@@ -66,9 +68,13 @@ k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* _
         const int n_inner = __popc(__ballot_sync(0xffffffffu, inner));
         if (n_inner > walk_min) {
             if (inner) {
-                node_step<COUNT>(sv, T, stack, tc);
-                // a second step on the same vote (the vote costs about a quarter of a step)
-                if (n_inner > walk_min + 4 && PT_IS_INNER(T.cur)) node_step<COUNT>(sv, T, stack, tc);
+                if (WIDE) {
+                    node_step4<COUNT>(sv, T, stack, tc);
+                } else {
+                    node_step<COUNT>(sv, T, stack, tc);
+                    // a second step on the same vote (the vote costs about a quarter of a step)
+                    if (n_inner > walk_min + 4 && PT_IS_INNER(T.cur)) node_step<COUNT>(sv, T, stack, tc);
+                }
             }
             continue;
         }
@@ -373,23 +379,30 @@ int pt_trace_persist(PtContext* ctx, const PtScene* s, const float4* rays, long 
     return PT_OK;
 }
 
-int pt_render_persist(PtContext* ctx, const PtScene* s, const RenderConsts& rc, bool legacy, bool count, float4* accum,
-                      float4* accum_sq, int shade_min, int serve_min) {
-    cudaStream_t st = ctx->stream;
-    int blocks = 0, rcb;
-    if (legacy) rcb = count ? resident_blocks(ctx, k_paths_persist<true, true>, &blocks) : resident_blocks(ctx, k_paths_persist<true, false>, &blocks);
-    else rcb = count ? resident_blocks(ctx, k_paths_persist<false, true>, &blocks) : resident_blocks(ctx, k_paths_persist<false, false>, &blocks);
+template <bool LEGACY, bool COUNT, bool WIDE>
+static int launch_persist(PtContext* ctx, const PtScene* s, const RenderConsts& rc, float4* accum, float4* accum_sq, int shade_min,
+                          int serve_min) {
+    int blocks = 0;
+    int rcb = resident_blocks(ctx, k_paths_persist<LEGACY, COUNT, WIDE>, &blocks);
     if (rcb) return rcb;
     const unsigned long long need = (rc.total_paths + PT_BLOCK - 1) / PT_BLOCK;
     if ((unsigned long long)blocks > need) blocks = (int)need;
     if (blocks < 1) return PT_OK;
-    if (legacy) {
-        if (count) k_paths_persist<true, true><<<blocks, PT_BLOCK, 0, st>>>(s->view, rc, ctx->counters, accum, accum_sq, shade_min, serve_min);
-        else k_paths_persist<true, false><<<blocks, PT_BLOCK, 0, st>>>(s->view, rc, ctx->counters, accum, accum_sq, shade_min, serve_min);
-    } else {
-        if (count) k_paths_persist<false, true><<<blocks, PT_BLOCK, 0, st>>>(s->view, rc, ctx->counters, accum, accum_sq, shade_min, serve_min);
-        else k_paths_persist<false, false><<<blocks, PT_BLOCK, 0, st>>>(s->view, rc, ctx->counters, accum, accum_sq, shade_min, serve_min);
-    }
+    k_paths_persist<LEGACY, COUNT, WIDE><<<blocks, PT_BLOCK, 0, ctx->stream>>>(s->view, rc, ctx->counters, accum, accum_sq, shade_min, serve_min);
     PT_CUDA(cudaGetLastError());
     return PT_OK;
+}
+
+int pt_render_persist(PtContext* ctx, const PtScene* s, const RenderConsts& rc, bool legacy, bool count, float4* accum,
+                      float4* accum_sq, int shade_min, int serve_min, bool wide) {
+    if (wide) {  // experimental: the node phase walks the 4-wide copy of the tree
+        if (legacy) return count ? launch_persist<true, true, true>(ctx, s, rc, accum, accum_sq, shade_min, serve_min)
+                                 : launch_persist<true, false, true>(ctx, s, rc, accum, accum_sq, shade_min, serve_min);
+        return count ? launch_persist<false, true, true>(ctx, s, rc, accum, accum_sq, shade_min, serve_min)
+                     : launch_persist<false, false, true>(ctx, s, rc, accum, accum_sq, shade_min, serve_min);
+    }
+    if (legacy) return count ? launch_persist<true, true, false>(ctx, s, rc, accum, accum_sq, shade_min, serve_min)
+                             : launch_persist<true, false, false>(ctx, s, rc, accum, accum_sq, shade_min, serve_min);
+    return count ? launch_persist<false, true, false>(ctx, s, rc, accum, accum_sq, shade_min, serve_min)
+                 : launch_persist<false, false, false>(ctx, s, rc, accum, accum_sq, shade_min, serve_min);
 }

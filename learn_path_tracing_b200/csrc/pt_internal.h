@@ -166,7 +166,7 @@ int pt_quantize_nodes(PtContext* ctx, const float4* d_nodes, int64_t n_nodes, co
 // persist.cu — persistent while-while kernels (PT_MODE_PERSIST)
 struct RenderConsts;
 int pt_render_persist(PtContext* ctx, const PtScene* s, const RenderConsts& rc, bool legacy, bool count, float4* accum,
-                      float4* accum_sq, int shade_min, int serve_min);
+                      float4* accum_sq, int shade_min, int serve_min, bool wide = false);
 int pt_trace_persist(PtContext* ctx, const PtScene* s, const float4* rays, long long n, float4* hits, bool count,
                      bool sort, bool use_qnodes, int serve_min, int fetch_min, cudaEvent_t ev_sorted, bool wide = false);
 // dual.cu — persistent kernel with a lane-private parking place per lane (PT_MODE_DUAL)

@@ -510,7 +510,9 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
         const int shade_min = p->reserved[2] > 0 ? p->reserved[2] : 22;
         const int serve_min = p->reserved[3] > 0 ? p->reserved[3] : 8;
         if (timing) cudaEventRecord(get_event(ctx, ev_idx++), st);
-        rcode = pt_render_persist(ctx, s, rc, legacy, count, (float4*)accum_dev, (float4*)accum_sq_dev, shade_min, serve_min);
+        const bool wide = (p->flags & PT_FLAG_WIDE) != 0;
+        PT_REQUIRE(!wide || s->view.wnodes, "PT_FLAG_WIDE: the scene has no 4-wide tree (build it with PT_WIDE=1 in the environment)");
+        rcode = pt_render_persist(ctx, s, rc, legacy, count, (float4*)accum_dev, (float4*)accum_sq_dev, shade_min, serve_min, wide);
         if (timing) cudaEventRecord(get_event(ctx, ev_idx++), st);
         iterations = 1; launches = 1;
     } else if (mode == PT_MODE_SPLIT)

@@ -364,6 +364,32 @@ def test_wide_tree_traversal_returns_identical_hit_records(ctx, monkeypatch):
         ctx.trace_batch_device(sc2, rays.data_ptr(), 1000, c.data_ptr(), L.PT_FLAG_TRACE_WIDE)
 
 
+@pytest.mark.skipif(os.environ.get("PT_TEST_WIDE_RENDER") != "1",
+                    reason="4-wide walk inside k_paths_persist: written at the end of round 1, not yet run on a GPU (opt in with PT_TEST_WIDE_RENDER=1)")
+@pytest.mark.parametrize("name", ["10_final", "legacy_synthetic"])
+def test_wide_tree_render_traces_the_same_paths(ctx, monkeypatch, name):
+    """k_paths_persist<.., WIDE>: same RNG keys, same closest hits -> the same paths as the binary-tree kernel."""
+    monkeypatch.setenv("PT_WIDE", "1")
+    if name == "10_final":
+        W, H = 160, 90
+        world, cam = scenes.scene_10_final((W, H))
+        model, kw = L.PT_SHADE_V2, {}
+    else:
+        from helpers import synthetic_legacy_world
+        world, cam = synthetic_legacy_world()
+        W, H = cam.resolution
+        model, kw = L.PT_SHADE_LEGACY, {"absorptivity": 0.25}
+    sc = world.device_scene(ctx)
+    a, b = L.Renderer(W, H, ctx), L.Renderer(W, H, ctx)
+    sa = a.render(sc, cam.to_struct(), 32, 32, model, seed=5, flags=L.PT_FLAG_COUNTERS, **kw)
+    sb = b.render(sc, cam.to_struct(), 32, 32, model, seed=5, flags=L.PT_FLAG_COUNTERS | L.PT_FLAG_WIDE, **kw)
+    assert sa.paths == sb.paths and abs(int(sa.segments) - int(sb.segments)) <= 1e-3 * sa.segments
+    assert np.array_equal(a.accum.cpu().numpy()[:, 3], b.accum.cpu().numpy()[:, 3])
+    assert np.allclose(a.mean(), b.mean(), rtol=2e-3, atol=2e-4)
+    assert sb.nodes_visited < 0.85 * sa.nodes_visited, (sa.nodes_visited, sb.nodes_visited)
+    print(f"{name}: wide {sb.nodes_visited / sb.segments:.2f} steps/segment vs {sa.nodes_visited / sa.segments:.2f}")
+
+
 def test_host_trace_pipeline_equals_device_path(ctx):
     """pt_trace_batch (host rays in, host ids/t out): the chunked three-stream pipeline (staging threads, H2D | sort +
     trace + unpack | D2H) returns exactly what one pt_trace_batch_device call over the whole batch returns — several
