@@ -67,10 +67,11 @@ extern "C" {
                                    entry-point/direction Morton order; results always land in batch order) */
 #define PT_FLAG_TRACE_SIMPLE 16 /* one ray per thread (k_trace) instead of the persistent while-while warps */
 #define PT_FLAG_NO_QNODES 32    /* walk the 64-byte float nodes even when the tree has the 32-byte quantised copy */
-#define PT_FLAG_TRACE_WIDE 128  /* EXPERIMENTAL: walk the 4-wide copy of the tree (scene built with PT_WIDE=1 in the
-                                   environment; csrc/bvh4.h); same hit records, fewer steps                        */
-#define PT_FLAG_WIDE PT_FLAG_TRACE_WIDE /* the same for pt_render (PtRenderParams.flags, persistent mode only): validated in
-                                   pt_trace_batch_device on the B200, NOT YET RUN in the render kernel                 */
+#define PT_FLAG_TRACE_WIDE 128  /* `make EXPERIMENTAL=1` builds only: walk the 4-wide copy of the tree (scene built with
+                                   PT_WIDE=1 in the environment; csrc/bvh4.h).  Same hit records, 0.57x the steps, but
+                                   measured 5-9 % slower on the render workloads and 40 % slower on the 10 M-triangle
+                                   batch (profiles/r02_ab_wide.txt): not in the default library (PT_ERR_INVALID)      */
+#define PT_FLAG_WIDE PT_FLAG_TRACE_WIDE /* the same for pt_render (PtRenderParams.flags, persistent mode only)       */
 /* bits 8-13 of the trace flags: lanes that must wait before a warp services them (0 = default 8);
    bits 14-19: finished lanes that trigger result write-back + refill (0 = default 8) */
 
@@ -111,11 +112,13 @@ typedef struct PtRenderParams {
     int32_t flags;          /* PT_FLAG_*                                                            */
     int32_t reserved[6];    /* [0] wavefront mode: 0 auto (= 3), 1 split (k_extend +
                                    k_shade per bounce), 2 fused K-step (k_paths), 3 persistent ballot-scheduled (k_paths_persist),
-                                   4 experimental: persistent + block-local shading queues (k_paths_queue, slower)
-                                   5 experimental: persistent + two lane-private path records per lane (k_paths_dual, slower)
+                                   4, 5: `make EXPERIMENTAL=1` builds only (k_paths_queue: block-local shading queues;
+                                   k_paths_dual: two lane-private path records per lane; both measured slower)
                                [1] fused mode: ray segments per path slot per launch (0 = default 32); mode 5: blocks per SM (3 or 4)
                                [2] persistent mode: finished lanes that trigger shading + refill (0 = default 22)
-                               [3] persistent mode: waiting lanes that trigger a service (leaf tests) (0 = default 8)  */
+                               [3] persistent mode: waiting lanes that trigger a service (leaf tests) (0 = default 8)
+                               [4], [5] persistent mode: render only the rows [row0, row1) of the frame (0, 0 = all);
+                                   the multi-GPU path renders band by band and reduces band k while band k+1 renders */
 } PtRenderParams; /* 64 bytes */
 
 typedef struct PtStats {
@@ -211,9 +214,13 @@ int pt_random_rays_device(PtContext* ctx, void* rays_dev, int64_t n, uint32_t se
 /* Render params->spp samples of every pixel and ADD the radiance into accum_dev (float4[h*w]:
  * sum r, g, b, and number of contributing paths); accum_sq_dev (float4[h*w], sum of squares) is
  * optional.  The caller zeroes the buffers (progressive rendering keeps adding, 15_module.py:1022-1036).
- * Asynchronous on the context stream apart from a few small counter read-backs.                 */
+ * stats == NULL: fully ASYNCHRONOUS on the context stream (persistent / queue modes: one kernel launch and one small
+ * counter copy are enqueued and the call returns; whatever the caller enqueues next on that stream — an NCCL reduce,
+ * pt_postprocess — follows without a host round trip).  stats != NULL: the call ends with pt_render_stats().   */
 int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, const PtRenderParams* p, void* accum_dev,
               void* accum_sq_dev, PtStats* stats);
+/* Statistics of the LAST pt_render on this context; waits for that render (not for later work on the stream). */
+int pt_render_stats(PtContext* ctx, PtStats* stats);
 
 /* Same through host buffers: accum_host[width][height][3] (Taichi field layout, sum of radiance,
  * overwritten), accum_sq_host optional.  Includes device allocation, render, device->host copy. */
@@ -234,6 +241,8 @@ int pt_measure_fp32_peak(PtContext* ctx, float* tflops);
 
 const char* pt_last_error(void);
 int pt_version(void);
+/* "sm_100a experimental=0|1": whether the library was built with `make EXPERIMENTAL=1` (render modes 4/5, PT_FLAG_WIDE). */
+const char* pt_build_info(void);
 
 #ifdef __cplusplus
 }

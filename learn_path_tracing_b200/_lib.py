@@ -23,16 +23,16 @@ PT_SHADE_V2_NORMALS = 3
 PT_FLAG_ACCUM_SQ = 1
 PT_FLAG_TIMING = 2
 PT_FLAG_COUNTERS = 4
-PT_FLAG_TRACE_WIDE = 128  # experimental 4-wide traversal (scene built with PT_WIDE=1)
-PT_FLAG_WIDE = PT_FLAG_TRACE_WIDE  # the same bit in PtRenderParams.flags (persistent mode; not yet run on a GPU)
+PT_FLAG_TRACE_WIDE = 128  # `make EXPERIMENTAL=1` builds only: 4-wide traversal (scene built with PT_WIDE=1); measured slower
+PT_FLAG_WIDE = PT_FLAG_TRACE_WIDE  # the same bit in PtRenderParams.flags (persistent mode)
 PT_FLAG_PIXEL_GRID = 64  # stages 2-4 camera: lattice rays i/(W-1), j/(H-1), no jitter
 
 PT_MODE_AUTO = 0
 PT_MODE_SPLIT = 1   # classic wavefront: k_extend + k_shade per bounce, pool refilled by an atomic counter
 PT_MODE_FUSED = 2   # k_paths: K segments per launch in registers, compaction at write-back (the HBM path-pool wavefront)
 PT_MODE_PERSIST = 3  # k_paths_persist: persistent while-while lanes, one launch per render (auto)
-PT_MODE_QUEUE = 4    # k_paths_queue: persistent lanes + block-local shading queues in shared memory
-PT_MODE_DUAL = 5     # k_paths_dual: persistent lanes with a lane-private parking place (two paths per lane)
+PT_MODE_QUEUE = 4    # `make EXPERIMENTAL=1` builds only: persistent lanes + block-local shading queues in shared memory
+PT_MODE_DUAL = 5     # `make EXPERIMENTAL=1` builds only: persistent lanes with a lane-private parking place
 PT_FLAG_NO_SORT = 8        # pt_trace_batch_device: keep batch order
 PT_FLAG_TRACE_SIMPLE = 16  # pt_trace_batch_device: one ray per thread (k_trace)
 PT_FLAG_NO_QNODES = 32     # pt_trace_batch_device: 64-byte float nodes even when the quantised copy exists
@@ -83,6 +83,7 @@ API_SYMBOLS = [
     "pt_scene_bvh_download", "pt_scene_triangles_download", "pt_generate_rays", "pt_trace_batch",
     "pt_trace_batch_device", "pt_random_rays_device", "pt_render", "pt_render_host", "pt_postprocess",
     "pt_postprocess_host", "pt_download_accum", "pt_measure_fp32_peak", "pt_last_error", "pt_version",
+    "pt_render_stats", "pt_build_info",
 ]
 
 
@@ -141,6 +142,8 @@ def load():
         "pt_measure_fp32_peak": (i32, [vp, P(f32)]),
         "pt_last_error": (C.c_char_p, []),
         "pt_version": (i32, []),
+        "pt_render_stats": (i32, [vp, P(PtStats)]),
+        "pt_build_info": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
@@ -148,6 +151,11 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def has_experimental() -> bool:
+    """True when the loaded library was built with `make EXPERIMENTAL=1` (render modes 4/5, PT_FLAG_WIDE)."""
+    return b"experimental=1" in load().pt_build_info()
 
 
 def host_image(width: int, height: int) -> np.ndarray:
@@ -228,10 +236,18 @@ class Context:
         check(self.lib.pt_random_rays_device(self.handle, C.c_void_p(rays_ptr), n, seed))
 
     def render(self, scene: "Scene", cam: PtCamera, params: PtRenderParams, accum_ptr: int,
-               accum_sq_ptr: int | None = None) -> PtStats:
-        st = PtStats()
+               accum_sq_ptr: int | None = None, want_stats: bool = True) -> PtStats | None:
+        """pt_render.  want_stats=False: nothing waits for the GPU — the call returns as soon as the kernel is enqueued on
+        the context's stream (ask render_stats() later); the multi-GPU path chains its reduce behind it that way."""
+        st = PtStats() if want_stats else None
         check(self.lib.pt_render(self.handle, scene.handle, C.byref(cam), C.byref(params), C.c_void_p(accum_ptr),
-                                 C.c_void_p(accum_sq_ptr or 0), C.byref(st)))
+                                 C.c_void_p(accum_sq_ptr or 0), C.byref(st) if want_stats else None))
+        return st
+
+    def render_stats(self) -> PtStats:
+        """Statistics of the last render() on this context (waits for that render only)."""
+        st = PtStats()
+        check(self.lib.pt_render_stats(self.handle, C.byref(st)))
         return st
 
     def render_host(self, scene: "Scene", cam: PtCamera, params: PtRenderParams, want_sq: bool = False):

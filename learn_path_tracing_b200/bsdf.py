@@ -1,7 +1,7 @@
 """BSDF selectors of taichi_pathtracer (10_final/bsdf.py:62-110, 6_diffuse/bsdf.py:20-26).
 
 In the reference these classes hold @ti.func device code and are chosen inside propagate_once
-(__main__.py:65-75).  Here the scattering code is hand-written CUDA (csrc/shade_v2.cuh); the classes
+(__main__.py:65-75).  Here the scattering code is hand-written CUDA (csrc/shade.cuh:scatter_v2); the classes
 remain as the names driver scripts import and carry the shading-model id handed to pt_render.
 """
 from . import _lib

@@ -1,7 +1,7 @@
 """Camera of taichi_pathtracer stages 6-10 (10_final/camera.py:38-93).
 
 Same constructor, setters and angle conventions (degrees, yaw*pitch*roll).  The per-pixel work of
-Camera.get_rays runs on the device (csrc/raygen.cuh); the host only derives the basis.
+Camera.get_rays runs on the device (csrc/shade.cuh:camera_ray, fused into the path kernel); the host only derives the basis.
 """
 from __future__ import annotations
 

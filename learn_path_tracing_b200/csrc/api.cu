@@ -23,6 +23,13 @@ void pt_set_error(const char* fmt, ...) {
 
 extern "C" const char* pt_last_error(void) { return g_err; }
 extern "C" int pt_version(void) { return PT_API_VERSION; }
+extern "C" const char* pt_build_info(void) {
+#ifdef PT_EXPERIMENTAL
+    return "sm_100a experimental=1";
+#else
+    return "sm_100a experimental=0";
+#endif
+}
 
 // ---- context ---------------------------------------------------------------------------------
 extern "C" int pt_context_create(int device, void* stream, PtContext** out) {
@@ -75,6 +82,7 @@ extern "C" void pt_context_destroy(PtContext* c) {
     if (c->stage_out) cudaStreamDestroy(c->stage_out);
     if (c->counters) cudaFree(c->counters);
     if (c->counters_host) cudaFreeHost(c->counters_host);
+    if (c->stats_host) cudaFreeHost(c->stats_host);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     for (int k = 0; k < 4; ++k)
@@ -206,6 +214,8 @@ extern "C" int pt_scene_add_mesh(PtScene* s, const float* pos, int nv, const flo
                                  const int32_t* faces, int nf) {
     PT_REQUIRE(s && pos && nrm && uv && faces && nv > 0 && nn > 0 && nt > 0 && nf >= 0, "bad argument");
     PT_REQUIRE(!s->device_generated_tris, "scene already holds device-generated triangles");
+    PT_REQUIRE(s->h_tri_shade.size() == 16 * (size_t)s->n_tri,
+               "scene already holds a raw triangle soup (pt_scene_set_triangles): meshes and soups do not mix");
     for (int f = 0; f < nf; ++f) {
         const int32_t* F = faces + 10 * (size_t)f;
         for (int k = 0; k < 3; ++k)
@@ -431,7 +441,11 @@ static Box host_prim_box(const PtScene* s, int64_t p) {
 // are tested in insertion order like the reference's World.hit loop.
 static void select_global_prims(PtScene* s, int64_t n_total, std::vector<int32_t>& global) {
     global.clear();
-    if (s->device_generated_tris) return;
+    if (s->device_generated_tris) {  // no host copy to measure; a single triangle needs no tree
+        if (n_total < 2)
+            for (int64_t p = 0; p < n_total; ++p) global.push_back((int32_t)p);
+        return;
+    }
     if (n_total <= 8) {
         for (int64_t p = 0; p < n_total; ++p) global.push_back((int32_t)p);
         return;
@@ -475,8 +489,9 @@ extern "C" int pt_scene_build(PtScene* s) {
     const int64_t n_sph = (int64_t)s->h_sph_cr.size() / 4;
     const int64_t n_tri = s->n_tri;
     const int64_t n_total = n_sph + n_tri;
-    PT_REQUIRE(n_total > 0, "empty scene");
+    // an empty World() is a valid scene (2_camera_and_ray/__main__.py:26-28 renders the bare sky): every ray misses
     PT_REQUIRE(n_total < (1ll << 31), "too many primitives");
+    PT_REQUIRE(s->h_tri_shade.empty() || s->h_tri_shade.size() == 16 * (size_t)n_tri, "triangle shading records out of step");
 
     float4* keep_geo = s->device_generated_tris ? s->d_tri_geo : nullptr;
     if (keep_geo) s->d_tri_geo = nullptr;
@@ -534,8 +549,17 @@ extern "C" int pt_scene_build(PtScene* s) {
     std::vector<int32_t> listed;
     SceneView& vw = s->view;
     vw.n_inl = 0;
+    vw.n_inl_tri = 0;
     for (int32_t p : s->h_global) {
-        if (p < n_sph && vw.n_inl < PT_MAX_INLINE) {
+        if (p >= n_sph && vw.n_inl_tri < PT_MAX_INLINE_TRI && !s->h_tri9.empty() && !getenv("PT_NO_INLINE_TRIS")) {
+            // same values as k_tri_geo_from_verts writes into tri_geo (IEEE single subtraction on either side)
+            const int k = vw.n_inl_tri++;
+            const float* v = &s->h_tri9[9 * (size_t)(p - n_sph)];
+            vw.inl_tri_id[k] = p;
+            vw.inl_tri[k][0] = make_float4(v[0], v[1], v[2], 0.0f);
+            vw.inl_tri[k][1] = make_float4(v[3] - v[0], v[4] - v[1], v[5] - v[2], 0.0f);
+            vw.inl_tri[k][2] = make_float4(v[6] - v[0], v[7] - v[1], v[8] - v[2], 0.0f);
+        } else if (p < n_sph && vw.n_inl < PT_MAX_INLINE) {
             const int k = vw.n_inl++;
             const float* c = &s->h_sph_cr[4 * (size_t)p];
             vw.inl_id[k] = p;
@@ -598,6 +622,7 @@ extern "C" int pt_scene_build(PtScene* s) {
     }
     // EXPERIMENTAL (PT_WIDE=1): 4-wide copy of the tree, collapsed on the host (bvh4.h), for k_trace_persist<.., WIDE>
     s->view.wnodes = nullptr;
+#ifdef PT_EXPERIMENTAL
     {
         const char* wenv = getenv("PT_WIDE");
         if (wenv && wenv[0] == '1' && root != PT_NO_BVH && s->n_nodes > 0) {
@@ -611,6 +636,7 @@ extern "C" int pt_scene_build(PtScene* s) {
             s->view.wnodes = s->d_wnodes;
         }
     }
+#endif
     SceneView& v = s->view;
     v.sph_cr = s->d_sph_cr; v.sph_aux = s->d_sph_aux; v.sph_mat = s->d_sph_mat;
     v.tri_geo = s->d_tri_geo; v.tri_shade = s->d_tri_shade;

@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(D_BLOCK, MINB)
 k_paths_dual(const SceneView sv, const RenderConsts rc, unsigned long long* __restrict__ counters,
              float4* __restrict__ accum, float4* __restrict__ accum_sq, int shade_min, int serve_min) {
     __shared__ DShared S;
-    int stack[PT_STACK];
+    int lstack[PT_STACK];
+    const TStack<0> stack = {nullptr, lstack};  // experimental kernel form: plain local-memory stack
     const unsigned tid = threadIdx.x, lane = tid & 31u;
     const unsigned lt = (1u << lane) - 1u;
     const unsigned tiles_x = ((unsigned)rc.W + D_TILE_W - 1) / D_TILE_W, tiles_y = ((unsigned)rc.H + D_TILE_H - 1) / D_TILE_H;
@@ -125,7 +126,7 @@ k_paths_dual(const SceneView sv, const RenderConsts rc, unsigned long long* __re
                         atomicAdd(&accum[q.pixel], make_float4(c.x, c.y, c.z, 1.0f));
                         if (rc.accum_sq) atomicAdd(&accum_sq[q.pixel], make_float4(c.x * c.x, c.y * c.y, c.z * c.z, 1.0f));
                     } else {
-                        if (LEGACY) scatter_legacy(sv, q, hh, rc.absorptivity, rc.seed);
+                        if (LEGACY) scatter_legacy(sv, q, hh, rc.absorptivity, rc.seed, sv.lut);
                         else scatter_v2(sv, q, hh, rc.shading_model, rc.seed);
                         q.bounce += 1u;
                         if (q.bounce < (uint32_t)rc.max_depth) {  // over propagate_limit: contributes nothing

@@ -74,6 +74,23 @@ PT_DEV void test_prim(const SceneView& sv, int p, float3 o, float3 d, float tmin
     }
 }
 
+// "global" triangles (the two halves of a ground plane) from the kernel parameter bank, like the inline spheres: every
+// segment of a legacy scene tests them first, so their operands are constant-bank reads instead of an index load and
+// three 128-bit loads per lane and segment.  Same arithmetic and tie rule as test_prim.
+template <bool COUNT>
+PT_DEV void test_inline_tris(const SceneView& sv, float3 o, float3 d, float tmin, Hit& h, float& best, TraceCounters& tc) {
+    for (int g = 0; g < sv.n_inl_tri; ++g) {
+        if (COUNT) tc.prims++;
+        float t, u, v;
+        const int p = sv.inl_tri_id[g];
+        const bool ok = triangle_hit_mt(o, d, f3(sv.inl_tri[g][0]), f3(sv.inl_tri[g][1]), f3(sv.inl_tri[g][2]), &t, &u, &v);
+        if (ok && t >= tmin && (t < best || (t == best && p < h.prim))) {
+            best = t;
+            h.t = t; h.prim = p; h.u = u; h.v = v;
+        }
+    }
+}
+
 // Ordered traversal with best-t pruning and an explicit stack (LBVH depth is bounded by the 63 Morton
 // bits + log2 of duplicate runs; 64 entries cover every tree the builder can emit for < 2^31 prims).
 template <bool COUNT>
@@ -95,6 +112,7 @@ PT_DEV Hit closest_hit(const SceneView& sv, float3 o, float3 d, float tmin, floa
             }
         }
     }
+    test_inline_tris<COUNT>(sv, o, d, tmin, h, best, tc);
     for (int g = 0; g < sv.n_global; ++g) test_prim<COUNT>(sv, __ldg(&sv.global_prims[g]), o, d, tmin, h, best, tc);
     if (sv.root == PT_NO_BVH) return h;
 
@@ -154,6 +172,35 @@ PT_DEV Hit closest_hit(const SceneView& sv, float3 o, float3 d, float tmin, floa
 // closest hit is order-independent.
 #define PT_SENTINEL PT_NO_BVH
 #define PT_STACK 64
+#ifndef PT_BLOCK
+#define PT_BLOCK 256
+#endif
+
+// Traversal stack.  ncu on round 1's kernels (profiles/r01_final_trace_persist_summary.txt, raw page): the per-thread
+// local-memory stack made up HALF of the L1 sectors of k_trace_persist (2.7 G loads + 2.9 G stores against 5.8 G sectors
+// of node/triangle fetches) and 93 GB of write-through traffic into L2 — lanes of a warp sit at different depths, so one
+// STL/LDL touches up to 32 lines — on a kernel whose L1 data pipe runs at 81 %.  The first NS entries of every lane
+// therefore live in SHARED memory, laid out [entry][thread]: a lane always hits its own bank whatever its depth, one
+// wavefront per warp instruction, nothing leaves the SM.  Deeper entries (rare: ordered traversal keeps the stack short)
+// spill to a small per-thread local array.  NS = 0 is the plain local stack (kernel forms that were not converted).
+template <int NS>
+struct TStack {
+    int* sm;   // &s_stack[0][threadIdx.x], stride PT_BLOCK
+    int* loc;  // local overflow, PT_STACK - NS entries (PT_STACK_WIDE - NS for the wide walk)
+};
+template <int NS>
+PT_DEV void st_push(const TStack<NS>& S, int& sp, int v) {
+    if (NS == 0) S.loc[sp] = v;
+    else if (sp < NS) S.sm[sp * PT_BLOCK] = v;
+    else S.loc[sp - NS] = v;
+    ++sp;
+}
+template <int NS>
+PT_DEV int st_pop(const TStack<NS>& S, int& sp) {
+    --sp;
+    if (NS == 0) return S.loc[sp];
+    return sp < NS ? S.sm[sp * PT_BLOCK] : S.loc[sp - NS];
+}
 
 struct Trav {
     float3 inv, oi;  // slab operands: t = box * inv + oi
@@ -182,27 +229,28 @@ PT_DEV void trav_prep(const SceneView& sv, float3 o, float3 d, float tmin, float
             h.t = t; h.prim = p;
         }
     }
+    test_inline_tris<COUNT>(sv, o, d, tmin, h, best, tc);
     for (int g = 0; g < sv.n_global; ++g) test_prim<COUNT>(sv, __ldg(&sv.global_prims[g]), o, d, tmin, h, best, tc);
 }
 
-template <bool COUNT>
-PT_DEV void trav_start(const SceneView& sv, float3 o, float3 d, float tmin, Trav& T, int* stack, TraceCounters& tc) {
+template <bool COUNT, int NS>
+PT_DEV void trav_start(const SceneView& sv, float3 o, float3 d, float tmin, Trav& T, const TStack<NS>& stack, TraceCounters& tc) {
     T.cur = sv.root;
     if (T.cur == PT_SENTINEL) return;  // tree-less scene (<= 8 primitives): the inline / global tests were everything
     T.inv = f3(1.0f / (fabsf(d.x) < 1e-18f ? copysignf(1e-18f, d.x) : d.x),
                1.0f / (fabsf(d.y) < 1e-18f ? copysignf(1e-18f, d.y) : d.y),
                1.0f / (fabsf(d.z) < 1e-18f ? copysignf(1e-18f, d.z) : d.z));
     T.oi = f3(-o.x * T.inv.x, -o.y * T.inv.y, -o.z * T.inv.z);
-    stack[0] = PT_SENTINEL;
-    T.sp = 1;
+    T.sp = 0;
+    st_push(stack, T.sp, PT_SENTINEL);
     if (T.cur < 0) {  // degenerate tree: the root is a leaf
         test_prim<COUNT>(sv, ~T.cur, o, d, tmin, T.h, T.best, tc);
         T.cur = PT_SENTINEL;
     }
 }
 
-template <bool COUNT>
-PT_DEV void trav_begin(const SceneView& sv, float3 o, float3 d, float tmin, float tmax, Trav& T, int* stack,
+template <bool COUNT, int NS>
+PT_DEV void trav_begin(const SceneView& sv, float3 o, float3 d, float tmin, float tmax, Trav& T, const TStack<NS>& stack,
                        TraceCounters& tc) {
     trav_prep<COUNT>(sv, o, d, tmin, tmax, T.best, T.h, tc);
     trav_start<COUNT>(sv, o, d, tmin, T, stack, tc);
@@ -224,11 +272,25 @@ PT_DEV Node8 ldg256(const void* p) {
 
 #define PT_IS_INNER(c) ((unsigned)(c) < (unsigned)PT_SENTINEL)
 
+// A lane that has just descended onto a leaf waits for the warp's next service before the primitive is tested
+// (persist.cu): its operands are asked into L1 meanwhile (PT_OPT_PREFETCH_LEAF).
+PT_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+PT_DEV void prefetch_prim(const SceneView& sv, int p) {
+    if (p < sv.n_sph) {
+        prefetch_l1(sv.sph_cr + p);
+        prefetch_l1(sv.sph_aux + p);
+    } else {
+        const float4* g = sv.tri_geo + 3 * (size_t)(p - sv.n_sph);
+        prefetch_l1(g);
+        prefetch_l1(g + 2);  // a 48-byte record may straddle two 128-byte lines
+    }
+}
+
 // One inner-node step of the ordered traversal: tests both child boxes of node T.cur, descends into the
 // nearer hit child (pushing the farther one) or pops.  Afterwards T.cur is an inner node, a leaf (< 0) or
 // PT_SENTINEL.
-template <bool COUNT>
-PT_DEV void node_step(const SceneView& sv, Trav& T, int* stack, TraceCounters& tc) {
+template <bool COUNT, int NS>
+PT_DEV void node_step(const SceneView& sv, Trav& T, const TStack<NS>& stack, TraceCounters& tc) {
     if (COUNT) tc.nodes++;
     const float4* n = sv.nodes + 4 * (size_t)T.cur;
     const Node8 A = ldg256(n), B = ldg256(n + 2);
@@ -248,13 +310,16 @@ PT_DEV void node_step(const SceneView& sv, Trav& T, int* stack, TraceCounters& t
     const int ca = __float_as_int(B.v[4]), cb = __float_as_int(B.v[5]);
     if (ha && hb) {
         const bool a_first = t0a <= t0b;
-        stack[T.sp++] = a_first ? cb : ca;
+        st_push(stack, T.sp, a_first ? cb : ca);
         T.cur = a_first ? ca : cb;
     } else if (ha || hb) {
         T.cur = ha ? ca : cb;
     } else {
-        T.cur = stack[--T.sp];
+        T.cur = st_pop(stack, T.sp);
     }
+#ifdef PT_OPT_PREFETCH_LEAF
+    if (T.cur < 0) prefetch_prim(sv, ~T.cur);
+#endif
 }
 
 // The same step on the 32-byte quantised nodes (one 256-bit load): the child boxes are 12 x u16 in the frame of the
@@ -278,8 +343,8 @@ PT_DEV QNode8 ldg256u(const void* p) {
 PT_DEV float qlo16(unsigned w) { return (float)(unsigned short)w; }
 PT_DEV float qhi16(unsigned w) { return (float)(unsigned short)(w >> 16); }
 
-template <bool COUNT>
-PT_DEV void node_step_q(const SceneView& sv, Trav& T, int* stack, TraceCounters& tc) {
+template <bool COUNT, int NS>
+PT_DEV void node_step_q(const SceneView& sv, Trav& T, const TStack<NS>& stack, TraceCounters& tc) {
     if (COUNT) tc.nodes++;
     const QNode8 N = ldg256u(sv.qnodes + 2 * (size_t)T.cur);
     // w0 = c0.min x|y, w1 = c0.min z | c0.max x, w2 = c0.max y|z, w3 = c1.min x|y, w4 = c1.min z | c1.max x, w5 = c1.max y|z
@@ -298,13 +363,16 @@ PT_DEV void node_step_q(const SceneView& sv, Trav& T, int* stack, TraceCounters&
     const int ca = (int)N.w[6], cb = (int)N.w[7];
     if (ha && hb) {
         const bool a_first = t0a <= t0b;
-        stack[T.sp++] = a_first ? cb : ca;
+        st_push(stack, T.sp, a_first ? cb : ca);
         T.cur = a_first ? ca : cb;
     } else if (ha || hb) {
         T.cur = ha ? ca : cb;
     } else {
-        T.cur = stack[--T.sp];
+        T.cur = st_pop(stack, T.sp);
     }
+#ifdef PT_OPT_PREFETCH_LEAF
+    if (T.cur < 0) prefetch_prim(sv, ~T.cur);
+#endif
 }
 
 // EXPERIMENTAL (opt-in, see bvh4.h; bit-identical hit records on the B200, 0.57x the steps, 1.32x on a small batch).
@@ -314,8 +382,8 @@ PT_DEV void node_step_q(const SceneView& sv, Trav& T, int* stack, TraceCounters&
 // kernel that uses it carries a 128-entry stack.
 #define PT_WIDE_EMPTY 0x7fffffff
 #define PT_STACK_WIDE 128
-template <bool COUNT>
-PT_DEV void node_step4(const SceneView& sv, Trav& T, int* stack, TraceCounters& tc) {
+template <bool COUNT, int NS>
+PT_DEV void node_step4(const SceneView& sv, Trav& T, const TStack<NS>& stack, TraceCounters& tc) {
     if (COUNT) tc.nodes++;
     const float4* n = sv.wnodes + 8 * (size_t)T.cur;
     const Node8 A = ldg256(n), B = ldg256(n + 2), C = ldg256(n + 4);
@@ -343,16 +411,16 @@ PT_DEV void node_step4(const SceneView& sv, Trav& T, int* stack, TraceCounters& 
     for (int k = 0; k < 4; ++k) {
         if (h[k]) {
             if (k == near) next = ref[k];
-            else stack[T.sp++] = ref[k];
+            else st_push(stack, T.sp, ref[k]);
         }
     }
     if (near >= 0) T.cur = next;
-    else T.cur = stack[--T.sp];
+    else T.cur = st_pop(stack, T.sp);
 }
 
 // Leaf step: tests primitive ~T.cur and pops.
-template <bool COUNT>
-PT_DEV void leaf_step(const SceneView& sv, float3 o, float3 d, float tmin, Trav& T, int* stack, TraceCounters& tc) {
+template <bool COUNT, int NS>
+PT_DEV void leaf_step(const SceneView& sv, float3 o, float3 d, float tmin, Trav& T, const TStack<NS>& stack, TraceCounters& tc) {
     test_prim<COUNT>(sv, ~T.cur, o, d, tmin, T.h, T.best, tc);
-    T.cur = stack[--T.sp];
+    T.cur = st_pop(stack, T.sp);
 }

@@ -267,6 +267,23 @@ __global__ void k_relayout(long long n_nodes, const float4* __restrict__ in, con
     o[0] = a; o[1] = b; o[2] = c; o[3] = k;
 }
 
+// Depth of a hierarchy (levels of inner nodes above the deepest leaf) from its parent array, one thread per leaf.  Every
+// candidate is measured: the traversal stacks hold PT_STACK entries and are not bounds-checked in the kernels.
+__global__ void k_tree_depth(long long n, const int* __restrict__ parent, int* __restrict__ max_depth) {
+    const long long leaf = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf >= n) return;
+    int depth = 0;
+    for (int c = parent[(n - 1) + leaf]; c >= 0; c = parent[c]) ++depth;
+    for (int o = 16; o > 0; o >>= 1) depth = max(depth, __shfl_xor_sync(0xffffffffu, depth, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(max_depth, depth);
+}
+// keys[i] = i: the Karras hierarchy over these is the binary radix tree of the sorted INDEX, at most 32 levels deep
+// whatever the geometry — the fallback when every real candidate is too deep for the traversal stack
+__global__ void k_index_keys(long long n, unsigned long long* __restrict__ keys) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = (unsigned long long)i;
+}
+
 // SAH cost of an emitted tree up to constants: the sum of the surface areas of every child box
 __global__ void k_sah_cost(const float4* __restrict__ nodes, long long n_nodes, double* __restrict__ cost) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -397,6 +414,10 @@ int pt_lbvh_build(PtContext* ctx, const float4* d_prim_aabb, const int* d_local_
     PT_CUDA(sc.alloc(&node_box, (size_t)(2 * (n - 1))));
     float4* nodes = nullptr;
     PT_CUDA(cudaMalloc(&nodes, (size_t)(n - 1) * 4 * sizeof(float4)));
+    struct NodesGuard {  // early error returns below must not leak the node array
+        float4** p; bool armed = true;
+        ~NodesGuard() { if (armed && *p) cudaFree(*p); }
+    } guard{&nodes};
 
     const int init[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000};
     PT_CUDA(cudaMemcpyAsync(bounds, init, sizeof init, cudaMemcpyHostToDevice, st));
@@ -420,9 +441,9 @@ int pt_lbvh_build(PtContext* ctx, const float4* d_prim_aabb, const int* d_local_
     size_t scan_bytes = 0;
     double* d_cost = nullptr;
     PT_CUDA(sc.alloc(&d_cost, 2));
-    int* d_depth = nullptr;  // deepest PLOC leaf when it exceeds PT_MAX_TREE_DEPTH, else 0
-    PT_CUDA(sc.alloc(&d_depth, 1));
-    PT_CUDA(cudaMemsetAsync(d_depth, 0, sizeof(int), st));
+    int* d_depth = nullptr;  // [slot] depth of the candidate built into that slot, [2] scratch of k_dfs_index
+    PT_CUDA(sc.alloc(&d_depth, 3));
+    PT_CUDA(cudaMemsetAsync(d_depth, 0, 3 * sizeof(int), st));
 
     // one hierarchy (Karras or PLOC) + refit into `out`; its SAH cost (sum of all child-box areas) into d_cost[slot]
     int *subtree = nullptr, *newid = nullptr;
@@ -431,8 +452,10 @@ int pt_lbvh_build(PtContext* ctx, const float4* d_prim_aabb, const int* d_local_
     const bool dfs = !(denv && denv[0] == '0');
     const char* renv = getenv("PT_PLOC_RADIUS");  // search radius in Morton order (A/B runs)
     const int radius = renv && atoi(renv) > 0 ? atoi(renv) : PT_PLOC_RADIUS;
-    auto build = [&](bool ploc, float4* out, int slot) -> int {
+    auto build = [&](bool ploc, float4* out, int slot, bool index_keys = false) -> int {
         PT_CUDA(cudaMemsetAsync(flags, 0, (size_t)(n - 1) * sizeof(int), st));
+        PT_CUDA(cudaMemsetAsync(d_depth + slot, 0, sizeof(int), st));
+        PT_CUDA(cudaMemsetAsync(d_cost + slot, 0, sizeof(double), st));
         if (ploc) {
             if (!nn) {
                 for (int b = 0; b < 2; ++b) {
@@ -460,9 +483,9 @@ int pt_lbvh_build(PtContext* ctx, const float4* d_prim_aabb, const int* d_local_
                 int c_new = 0;
                 PT_CUDA(cudaMemcpyAsync(&c_new, ctl + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
                 PT_CUDA(cudaStreamSynchronize(st));
-                if (c_new >= c || ++rounds > 4096) {  // cannot happen (the closest pair is always mutual)
-                    pt_set_error("pt_lbvh_build: PLOC made no progress (%d -> %d clusters)", c, c_new);
-                    return PT_ERR_CUDA;
+                if (c_new >= c || ++rounds > 4096) {  // chain-like inputs that merge one pair per round: not a candidate
+                    pt_set_error("pt_lbvh_build: PLOC gave up (%d -> %d clusters after %d rounds)", c, c_new, rounds);
+                    return PT_ERR_INVALID;
                 }
                 c = c_new;
                 cur ^= 1;
@@ -470,8 +493,10 @@ int pt_lbvh_build(PtContext* ctx, const float4* d_prim_aabb, const int* d_local_
             const int minus1 = -1;
             PT_CUDA(cudaMemcpy(parent, &minus1, sizeof(int), cudaMemcpyHostToDevice));  // the root (node 0) has no parent
         } else {
+            if (index_keys) k_index_keys<<<gridN, B, 0, st>>>(n, kb.Current());  // the Morton keys are not needed again
             k_hierarchy<<<(unsigned)((n - 1 + B - 1) / B), B, 0, st>>>(kb.Current(), n, children, parent);
         }
+        k_tree_depth<<<gridN, B, 0, st>>>(n, parent, d_depth + slot);
         if (ploc && dfs) {  // PLOC numbers nodes by merge round: renumber depth-first (see k_dfs_index)
             if (!subtree) {
                 PT_CUDA(sc.alloc(&subtree, (size_t)(n - 1)));
@@ -480,7 +505,7 @@ int pt_lbvh_build(PtContext* ctx, const float4* d_prim_aabb, const int* d_local_
             }
             const unsigned gi = (unsigned)((n - 1 + B - 1) / B);
             k_refit_emit<<<gridN, B, 0, st>>>(n, children, parent, vb.Current(), d_prim_aabb, node_box, flags, nodes_tmp, subtree);
-            k_dfs_index<<<gi, B, 0, st>>>(n - 1, children, parent, subtree, newid, d_depth);
+            k_dfs_index<<<gi, B, 0, st>>>(n - 1, children, parent, subtree, newid, d_depth + 2);
             k_relayout<<<gi, B, 0, st>>>(n - 1, nodes_tmp, newid, out);
         } else {
             k_refit_emit<<<gridN, B, 0, st>>>(n, children, parent, vb.Current(), d_prim_aabb, node_box, flags, out, nullptr);
@@ -533,36 +558,62 @@ int pt_lbvh_build(PtContext* ctx, const float4* d_prim_aabb, const int* d_local_
         PT_CUDA(cudaStreamSynchronize(st));
         return PT_OK;
     };
+    // every candidate's depth is measured (k_tree_depth): one that does not fit the traversal stack is not a candidate
+    auto depth_of = [&](int slot, int* out) -> int {
+        PT_CUDA(cudaMemcpy(out, d_depth + slot, sizeof(int), cudaMemcpyDeviceToHost));
+        return PT_OK;
+    };
+    bool have = false;  // `nodes` holds a tree of at most PT_MAX_TREE_DEPTH levels
+    int depth = 0;
     if (force && env[0] == 's') {
         double c = 0.0;
         rcb = host_sah(nodes, &c);
+        have = rcb == PT_OK && c < INFINITY;
     } else if (force || n > PT_PLOC_MAX) {
         rcb = build(force && env[0] == 'p', nodes, 0);
+        if (rcb == PT_OK) rcb = depth_of(0, &depth);
+        have = rcb == PT_OK && depth <= PT_MAX_TREE_DEPTH;
     } else {
         float4* nodes2 = nullptr;
         cudaError_t ea = cudaMalloc(&nodes2, (size_t)(n - 1) * 4 * sizeof(float4));
-        if (ea != cudaSuccess) { cudaFree(nodes); PT_CUDA(ea); }
+        PT_CUDA(ea);
+        double cost[2] = {INFINITY, INFINITY};
+        int dep[2] = {0, 0};
         rcb = build(false, nodes, 0);
-        if (rcb == PT_OK) rcb = build(true, nodes2, 1);
-        double cost[2] = {0.0, 0.0};
-        if (rcb == PT_OK && cudaMemcpy(cost, d_cost, sizeof cost, cudaMemcpyDeviceToHost) != cudaSuccess) rcb = PT_ERR_CUDA;
-        int ploc_depth = 0;
-        if (rcb == PT_OK && cudaMemcpy(&ploc_depth, d_depth, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) rcb = PT_ERR_CUDA;
-        if (ploc_depth > PT_MAX_TREE_DEPTH) cost[1] = INFINITY;  // would not fit the traversal stack: not a candidate
+        if (rcb == PT_OK) {
+            const int rcp = build(true, nodes2, 1);  // PLOC is an optional candidate: its failure keeps the Karras tree
+            if (cudaMemcpy(cost, d_cost, sizeof cost, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                cudaMemcpy(dep, d_depth, sizeof dep, cudaMemcpyDeviceToHost) != cudaSuccess) rcb = PT_ERR_CUDA;
+            if (rcp != PT_OK) {
+                cost[1] = INFINITY;
+                if (rcp == PT_ERR_CUDA) rcb = rcp;
+            }
+        }
+        for (int k = 0; k < 2; ++k)
+            if (dep[k] > PT_MAX_TREE_DEPTH) cost[k] = INFINITY;
         if (rcb == PT_OK && cost[1] < cost[0]) { std::swap(nodes, nodes2); cost[0] = cost[1]; }
         double cost_sah = -1.0;
         if (rcb == PT_OK && n <= PT_HOST_SAH_MAX) {  // tiny tree: a third candidate from the host (nodes2 is free again)
             rcb = host_sah(nodes2, &cost_sah);
-            if (rcb == PT_OK && cost_sah < cost[0]) std::swap(nodes, nodes2);
+            if (rcb == PT_OK && cost_sah < cost[0]) { std::swap(nodes, nodes2); cost[0] = cost_sah; }
         }
+        have = rcb == PT_OK && cost[0] < INFINITY;
         if (getenv("PT_BUILD_VERBOSE"))
-            fprintf(stderr, "[libb200pt] %lld prims: SAH cost best of lbvh/ploc %.6g (ploc %.6g), host sweep %.6g\n", (long long)n, cost[0], cost[1], cost_sah);
+            fprintf(stderr, "[libb200pt] %lld prims: SAH cost kept %.6g (lbvh depth %d, ploc %.6g depth %d, host sweep %.6g)\n",
+                    (long long)n, cost[0], dep[0], cost[1], dep[1], cost_sah);
         cudaFree(nodes2);
     }
-    if (rcb) {
-        cudaFree(nodes);
-        return rcb;
+    if (rcb == PT_OK && (!have || getenv("PT_FORCE_INDEX_TREE"))) {
+        // degenerate geometry (long runs of equal Morton codes, chains): the radix tree over the sorted index always fits
+        rcb = build(false, nodes, 0, true);
+        if (rcb == PT_OK) rcb = depth_of(0, &depth);
+        if (rcb == PT_OK && depth > PT_MAX_TREE_DEPTH) {
+            pt_set_error("pt_lbvh_build: index tree is %d levels deep", depth);
+            rcb = PT_ERR_INVALID;
+        }
     }
+    if (rcb) return rcb;  // the guard frees `nodes`
+    guard.armed = false;
     *d_nodes_out = nodes;
     *n_nodes_out = n - 1;
     *root_out = 0;

@@ -37,16 +37,43 @@
 #define PT_TILE_H 4
 #define PT_UNIT_SAMPLES 16
 
-// WIDE (experimental, opt-in: PT_WIDE=1 at build time + PT_FLAG_WIDE; NOT YET RUN ON A GPU in this kernel — the step
-// itself, extend.cuh:node_step4, is validated in k_trace_persist): the node phase walks the 4-wide copy of the tree.
+// WIDE (experimental, `make EXPERIMENTAL=1` + PT_WIDE=1 when the scene is built + PT_FLAG_WIDE): the node phase walks the
+// 4-wide copy of the tree (extend.cuh:node_step4).  Measured on the B200 in round 2 (profiles/r02_ab_wide.txt): same
+// images, 5-9 % SLOWER than the binary walk on every render workload, so it is not part of the default library.
+// Shared-memory traversal stack (extend.cuh:TStack), entries per lane.  Same-box A/B on the B200
+// (profiles/r02_ab_stack_lut_inline.txt): fixed-batch kernel 1649 (local stack) / 1673 (16 entries) / 1651 (24) / 1324
+// (32: one block per SM fewer) Mrays/s; render kernels 10_final 5880 (local) / 5828 (8) / 5802 (16) / 5825 (24), Yoimiya
+// within +-0.3 % — the stack traffic that fills half of the L1 sectors hits in L1 and is not what these kernels wait
+// for, and the shared form costs two predicated instructions per push/pop.  Hence: 16 entries for the batch kernel,
+// the plain local stack for the render kernels.
+#ifndef PT_SSTACK_RENDER
+#define PT_SSTACK_RENDER 0
+#endif
+#ifndef PT_SSTACK_TRACE
+#define PT_SSTACK_TRACE 16
+#endif
 template <bool LEGACY, bool COUNT, bool WIDE = false>
 __global__ void __launch_bounds__(PT_BLOCK, 4)
 k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* __restrict__ counters,
                 float4* __restrict__ accum, float4* __restrict__ accum_sq, int shade_min, int serve_min) {
-    int stack[WIDE ? PT_STACK_WIDE : PT_STACK];
+    constexpr int NS = WIDE ? 0 : PT_SSTACK_RENDER;
+    __shared__ int s_stack[NS ? NS : 1][PT_BLOCK];
+    int lstack[(WIDE ? PT_STACK_WIDE : PT_STACK) - NS];
+    const TStack<NS> stack = {&s_stack[0][threadIdx.x], lstack};
+#ifdef PT_OPT_GLOBAL_LUT
+    const float* lut = sv.lut;
+#else
+    // texture transfer tables (albedo^2.2 | x^2 | 2x-1, 3 KB) in shared memory for the lifetime of the block
+    __shared__ float s_lut[LEGACY ? 768 : 1];
+    if (LEGACY && sv.lut) {
+        for (int i = threadIdx.x; i < 768; i += PT_BLOCK) s_lut[i] = __ldg(sv.lut + i);
+        __syncthreads();
+    }
+    const float* lut = s_lut;
+#endif
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt = (1u << lane) - 1u;
-    const unsigned tiles_x = ((unsigned)rc.W + PT_TILE_W - 1) / PT_TILE_W, tiles_y = ((unsigned)rc.H + PT_TILE_H - 1) / PT_TILE_H;
+    const unsigned tiles_x = ((unsigned)rc.W + PT_TILE_W - 1) / PT_TILE_W, tiles_y = ((unsigned)(rc.row1 - rc.row0) + PT_TILE_H - 1) / PT_TILE_H;
     const unsigned spp = rc.sample_end - rc.spp_offset;
     const unsigned n_chunks = (spp + PT_UNIT_SAMPLES - 1) / PT_UNIT_SAMPLES;
     const unsigned long long n_units = (unsigned long long)tiles_x * tiles_y * n_chunks;
@@ -101,7 +128,7 @@ k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* _
                     st = ST_IDLE;
                 } else {
                     T.h.t = T.best;
-                    if (LEGACY) scatter_legacy(sv, p, T.h, rc.absorptivity, rc.seed);
+                    if (LEGACY) scatter_legacy(sv, p, T.h, rc.absorptivity, rc.seed, lut);
                     else scatter_v2(sv, p, T.h, rc.shading_model, rc.seed);
                     p.bounce += 1u;
                     st = p.bounce < (uint32_t)rc.max_depth ? ST_NEW : ST_IDLE;  // over propagate_limit: contributes nothing
@@ -127,7 +154,7 @@ k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* _
                     const unsigned tile = (unsigned)(u / n_chunks), chunk = (unsigned)(u - (unsigned long long)tile * n_chunks);
                     const unsigned ty = tile / tiles_x;
                     unit_x0 = (tile - ty * tiles_x) * PT_TILE_W;
-                    unit_y0 = ty * PT_TILE_H;
+                    unit_y0 = (unsigned)rc.row0 + ty * PT_TILE_H;
                     unit_s0 = chunk * PT_UNIT_SAMPLES;
                     unit_ns = min((unsigned)PT_UNIT_SAMPLES, spp - unit_s0);
                     unit_size = unit_ns * 32u;
@@ -139,7 +166,7 @@ k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* _
                     if (r < take) {
                         const unsigned q = unit_next + r;
                         const unsigned px = unit_x0 + (q & 7u), py = unit_y0 + ((q >> 3) & 3u);
-                        if (px < (unsigned)rc.W && py < (unsigned)rc.H) {  // image sizes need not be tile multiples
+                        if (px < (unsigned)rc.W && py < (unsigned)rc.row1) {  // image sizes / row bands need not be tile multiples
                             p.pixel = py * (unsigned)rc.W + px;
                             p.sample = rc.spp_offset + unit_s0 + (q >> 5);
                             p.bounce = 0u;
@@ -188,7 +215,10 @@ __global__ void __launch_bounds__(PT_BLOCK, WIDE ? 4 : 6)
 k_trace_persist(const SceneView sv, const float4* __restrict__ rays, const unsigned* __restrict__ order,
                 float4* __restrict__ hits, long long n, unsigned long long* __restrict__ counters, int serve_min,
                 int fetch_min) {
-    int stack[WIDE ? PT_STACK_WIDE : PT_STACK];
+    constexpr int NS = WIDE ? 0 : PT_SSTACK_TRACE;
+    __shared__ int s_stack[NS ? NS : 1][PT_BLOCK];
+    int lstack[(WIDE ? PT_STACK_WIDE : PT_STACK) - NS];
+    const TStack<NS> stack = {&s_stack[0][threadIdx.x], lstack};
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt = (1u << lane) - 1u;
     float3 o = f3(0, 0, 0), d = f3(0, 0, 1);
@@ -319,6 +349,18 @@ static int ensure_sort_scratch(PtContext* ctx, size_t bytes) {
 // Persistent grid: as many blocks as are resident at once.
 template <class K>
 static int resident_blocks(PtContext* ctx, K kernel, int* out) {
+    // Shared memory and L1 share 256 KB per SM: ask for exactly the carveout that the blocks the register budget allows
+    // (__launch_bounds__: 4 or 6 per SM) need for their stacks, the rest stays L1 for nodes and triangles.
+    static_assert(PT_SSTACK_TRACE * PT_BLOCK * 4 * 6 + 6 * 1024 <= 227 * 1024, "trace stacks exceed the shared memory of an SM");
+    static_assert(PT_SSTACK_RENDER * PT_BLOCK * 4 * 4 + 4 * 1024 <= 227 * 1024, "render stacks exceed the shared memory of an SM");
+    cudaFuncAttributes fa;
+    PT_CUDA(cudaFuncGetAttributes(&fa, kernel));
+    if (fa.sharedSizeBytes > 1024) {
+        const int by_regs = fa.numRegs > 0 ? 65536 / (fa.numRegs * PT_BLOCK) : 1;
+        const size_t want = (size_t)(by_regs < 1 ? 1 : by_regs) * (fa.sharedSizeBytes + 1024);
+        int pct = (int)((want * 100 + 228 * 1024 - 1) / (228 * 1024));
+        PT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct));
+    }
     int per_sm = 0;
     PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, PT_BLOCK, 0));
     if (per_sm < 1) per_sm = 1;
@@ -331,7 +373,7 @@ int pt_trace_persist(PtContext* ctx, const PtScene* s, const float4* rays, long 
     cudaStream_t st = ctx->stream;
     const unsigned* order = nullptr;
     if (sort && n > 1) {
-        PT_REQUIRE(n < (1ll << 32), "ray batches are limited to 2^32 - 1 rays");
+        PT_REQUIRE(n < (1ll << 31), "sorted ray batches are limited to 2^31 - 1 rays (cub::DeviceRadixSort takes an int count)");
         size_t tmp_bytes = 0;
         cub::DoubleBuffer<unsigned> kb(nullptr, nullptr), vb(nullptr, nullptr);
         PT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb, vb, (int)n, 0, 30, st));
@@ -350,6 +392,7 @@ int pt_trace_persist(PtContext* ctx, const PtScene* s, const float4* rays, long 
         order = vb.Current();
     }
     if (ev_sorted) PT_CUDA(cudaEventRecord(ev_sorted, st));
+#ifdef PT_EXPERIMENTAL
     if (wide) {  // experimental 4-wide walk (PT_FLAG_TRACE_WIDE): float nodes only
         int wblocks = 0;
         int rcw = count ? resident_blocks(ctx, k_trace_persist<true, false, true>, &wblocks) : resident_blocks(ctx, k_trace_persist<false, false, true>, &wblocks);
@@ -361,6 +404,9 @@ int pt_trace_persist(PtContext* ctx, const PtScene* s, const float4* rays, long 
         PT_CUDA(cudaGetLastError());
         return PT_OK;
     }
+#else
+    PT_REQUIRE(!wide, "the 4-wide walk is an experimental kernel form: rebuild with `make EXPERIMENTAL=1`");
+#endif
     int blocks = 0, rcb;
     const bool q = s->view.qnodes != nullptr && use_qnodes;
     if (count) rcb = q ? resident_blocks(ctx, k_trace_persist<true, true>, &blocks) : resident_blocks(ctx, k_trace_persist<true, false>, &blocks);
@@ -395,12 +441,16 @@ static int launch_persist(PtContext* ctx, const PtScene* s, const RenderConsts& 
 
 int pt_render_persist(PtContext* ctx, const PtScene* s, const RenderConsts& rc, bool legacy, bool count, float4* accum,
                       float4* accum_sq, int shade_min, int serve_min, bool wide) {
+#ifdef PT_EXPERIMENTAL
     if (wide) {  // experimental: the node phase walks the 4-wide copy of the tree
         if (legacy) return count ? launch_persist<true, true, true>(ctx, s, rc, accum, accum_sq, shade_min, serve_min)
                                  : launch_persist<true, false, true>(ctx, s, rc, accum, accum_sq, shade_min, serve_min);
         return count ? launch_persist<false, true, true>(ctx, s, rc, accum, accum_sq, shade_min, serve_min)
                      : launch_persist<false, false, true>(ctx, s, rc, accum, accum_sq, shade_min, serve_min);
     }
+#else
+    PT_REQUIRE(!wide, "the 4-wide walk is an experimental kernel form: rebuild with `make EXPERIMENTAL=1`");
+#endif
     if (legacy) return count ? launch_persist<true, true, false>(ctx, s, rc, accum, accum_sq, shade_min, serve_min)
                              : launch_persist<true, false, false>(ctx, s, rc, accum, accum_sq, shade_min, serve_min);
     return count ? launch_persist<false, true, false>(ctx, s, rc, accum, accum_sq, shade_min, serve_min)

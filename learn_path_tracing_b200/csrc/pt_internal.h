@@ -28,6 +28,7 @@
 //  env[W*H]           float4  x-major rgb
 // ---------------------------------------------------------------------------------------------
 #define PT_MAX_INLINE 8
+#define PT_MAX_INLINE_TRI 4
 struct SceneView {
     const float4* sph_cr;
     const float4* sph_aux;
@@ -59,6 +60,10 @@ struct SceneView {
     int inl_transparent[PT_MAX_INLINE];
     float inl_r2[PT_MAX_INLINE];
     float4 inl_cr[PT_MAX_INLINE];
+    // "global" TRIANGLES (ground plane halves) likewise: v0 | e1 | e2 as stored in tri_geo
+    int n_inl_tri;
+    int inl_tri_id[PT_MAX_INLINE_TRI];
+    float4 inl_tri[PT_MAX_INLINE_TRI][3];
     // EXPERIMENTAL 4-wide copy of the tree (bvh4.h: 8 float4 per node, root = 0), NULL unless the scene was built with
     // PT_WIDE=1 in the environment; only k_trace_persist<.., WIDE> reads it (PT_FLAG_TRACE_WIDE)
     const float4* wnodes;
@@ -76,6 +81,12 @@ struct PtContext {
     float4* hits = nullptr;
     unsigned long long* counters = nullptr;  // device: see wavefront.cu
     unsigned long long* counters_host = nullptr;  // pinned mirror ring
+    // counter block of the last pt_render (pinned) + what pt_render_stats needs to turn it into a PtStats
+    unsigned long long* stats_host = nullptr;
+    unsigned long long last_paths = 0;
+    int last_mode = 0, last_iterations = 0, last_launches = 0;
+    size_t last_ev_idx = 0;
+    bool last_timing = false, last_valid = false;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> ev_pool;

@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(Q_BLOCK, 4)
 k_paths_queue(const SceneView sv, const RenderConsts rc, unsigned long long* __restrict__ counters,
               float4* __restrict__ accum, float4* __restrict__ accum_sq, int serve_min) {
     __shared__ QShared S;
-    int stack[PT_STACK];
+    int lstack[PT_STACK];
+    const TStack<0> stack = {nullptr, lstack};  // experimental kernel form: plain local-memory stack
     const unsigned lane = threadIdx.x & 31u;
     const unsigned tiles_x = ((unsigned)rc.W + Q_TILE_W - 1) / Q_TILE_W, tiles_y = ((unsigned)rc.H + Q_TILE_H - 1) / Q_TILE_H;
     const unsigned spp = rc.sample_end - rc.spp_offset;
@@ -265,7 +266,7 @@ k_paths_queue(const SceneView sv, const RenderConsts rc, unsigned long long* __r
                     atomicAdd(&accum[p.pixel], make_float4(c.x, c.y, c.z, 1.0f));
                     if (rc.accum_sq) atomicAdd(&accum_sq[p.pixel], make_float4(c.x * c.x, c.y * c.y, c.z * c.z, 1.0f));
                 } else {
-                    if (LEGACY) scatter_legacy(sv, p, hh, rc.absorptivity, rc.seed);
+                    if (LEGACY) scatter_legacy(sv, p, hh, rc.absorptivity, rc.seed, sv.lut);
                     else scatter_v2(sv, p, hh, rc.shading_model, rc.seed);
                     p.bounce += 1u;
                     alive = p.bounce < (uint32_t)rc.max_depth;  // over propagate_limit: contributes nothing

@@ -153,24 +153,27 @@ struct Texel {
     float3 albedo, normal;
     float roughness, metallic;
 };
-PT_DEV void texel_accum(const SceneView& sv, int x, int y, float wgt, bool want_normal, Texel& o) {
+// `lut` = the three 256-entry transfer tables (albedo^2.2 | x^2 | 2x-1).  The persistent render kernel hands in its
+// SHARED-memory copy (3 KB per block, filled once per launch): round 1's ncu listing showed ~25 scalar global loads per
+// textured hit for them; the other kernel forms pass sv.lut (global).
+PT_DEV void texel_accum(const SceneView& sv, const float* lut, int x, int y, float wgt, bool want_normal, Texel& o) {
     if (x < 0 || y < 0 || x >= sv.tex_W || y >= sv.tex_H) return;  // outside the field: zero
     const uint2 q = __ldcg(&sv.atlas[(size_t)x * sv.tex_H + y]);  // L2 only: the atlas must not evict BVH nodes from L1
-    const float* la = sv.lut;
-    const float* ls = sv.lut + 256;
-    o.albedo.x = fmaf(wgt, __ldg(la + (q.x & 255u)), o.albedo.x);
-    o.albedo.y = fmaf(wgt, __ldg(la + ((q.x >> 8) & 255u)), o.albedo.y);
-    o.albedo.z = fmaf(wgt, __ldg(la + ((q.x >> 16) & 255u)), o.albedo.z);
-    o.roughness = fmaf(wgt, __ldg(ls + (q.x >> 24)), o.roughness);
-    o.metallic = fmaf(wgt, __ldg(ls + (q.y >> 24)), o.metallic);
+    const float* la = lut;
+    const float* ls = lut + 256;
+    o.albedo.x = fmaf(wgt, la[q.x & 255u], o.albedo.x);
+    o.albedo.y = fmaf(wgt, la[(q.x >> 8) & 255u], o.albedo.y);
+    o.albedo.z = fmaf(wgt, la[(q.x >> 16) & 255u], o.albedo.z);
+    o.roughness = fmaf(wgt, ls[q.x >> 24], o.roughness);
+    o.metallic = fmaf(wgt, ls[q.y >> 24], o.metallic);
     if (want_normal) {
-        const float* ln = sv.lut + 512;
-        o.normal.x = fmaf(wgt, __ldg(ln + (q.y & 255u)), o.normal.x);
-        o.normal.y = fmaf(wgt, __ldg(ln + ((q.y >> 8) & 255u)), o.normal.y);
-        o.normal.z = fmaf(wgt, __ldg(ln + ((q.y >> 16) & 255u)), o.normal.z);
+        const float* ln = lut + 512;
+        o.normal.x = fmaf(wgt, ln[q.y & 255u], o.normal.x);
+        o.normal.y = fmaf(wgt, ln[(q.y >> 8) & 255u], o.normal.y);
+        o.normal.z = fmaf(wgt, ln[(q.y >> 16) & 255u], o.normal.z);
     }
 }
-PT_DEV Texel sample_texture(const SceneView& sv, int id, float u, float v, bool want_normal) {
+PT_DEV Texel sample_texture(const SceneView& sv, const float* lut, int id, float u, float v, bool want_normal) {
     Texel o;
     o.albedo = f3(0, 0, 0); o.normal = f3(0, 0, 0); o.roughness = 0.0f; o.metallic = 0.0f;
     if (id < 0 || id >= sv.ntex) return o;
@@ -179,10 +182,10 @@ PT_DEV Texel sample_texture(const SceneView& sv, int id, float u, float v, bool 
         o.normal = f3(0.0f, 0.0f, 1.0f);
     }
     const Taps k = bilinear_taps(__ldg(&sv.tex_areas[id]), u, v);
-    texel_accum(sv, k.l, k.b, k.lb, want_normal, o);
-    texel_accum(sv, k.l, k.t, k.lt, want_normal, o);
-    texel_accum(sv, k.r, k.b, k.rb, want_normal, o);
-    texel_accum(sv, k.r, k.t, k.rt, want_normal, o);
+    texel_accum(sv, lut, k.l, k.b, k.lb, want_normal, o);
+    texel_accum(sv, lut, k.l, k.t, k.lt, want_normal, o);
+    texel_accum(sv, lut, k.r, k.b, k.rb, want_normal, o);
+    texel_accum(sv, lut, k.r, k.t, k.rt, want_normal, o);
     return o;
 }
 PT_DEV float3 env_fetch(const SceneView& sv, int x, int y) {
@@ -211,7 +214,8 @@ PT_DEV float3 sample_in_sphere(float u0, float u1, float u2) {  // 15_module.py:
 }
 
 // propagate_once hit branch (15_module.py:983-989) + gen_secondary_rays (:994-1013)
-PT_DEV void scatter_legacy(const SceneView& sv, PathState& p, const Hit& h, float absorptivity, uint32_t seed) {
+PT_DEV void scatter_legacy(const SceneView& sv, PathState& p, const Hit& h, float absorptivity, uint32_t seed,
+                           const float* lut) {
     const float3 d = p.d;
     const float3 point = p.o + h.t * d;
     float3 normal, albedo;
@@ -228,7 +232,7 @@ PT_DEV void scatter_legacy(const SceneView& sv, PathState& p, const Hit& h, floa
         const float theta = atan2f(-N.x, -N.z);
         const float uu = (theta * (1.0f / PT_PI) + 1.0f) * 0.5f;
         const float vv = phi * (1.0f / PT_PI) + 0.5f;
-        const Texel tx = sample_texture(sv, __float_as_int(aux.z), 2.0f * uu, vv, true);
+        const Texel tx = sample_texture(sv, lut, __float_as_int(aux.z), 2.0f * uu, vv, true);
         normal = normalize(tx.normal.x * T + tx.normal.y * B + tx.normal.z * N);
         albedo = tx.albedo; roughness = tx.roughness; metallic = tx.metallic;
         transparency = __float_as_int(aux.y);
@@ -239,7 +243,7 @@ PT_DEV void scatter_legacy(const SceneView& sv, PathState& p, const Hit& h, floa
         normal = normalize(w1 * f3(s0) + w2 * f3(s1) + w3 * f3(s2));
         const float uu = w1 * s0.w + w2 * s2.w + w3 * s3.y;
         const float vv = w1 * s1.w + w2 * s3.x + w3 * s3.z;
-        const Texel tx = sample_texture(sv, __float_as_int(s3.w), uu, vv, false);
+        const Texel tx = sample_texture(sv, lut, __float_as_int(s3.w), uu, vv, false);
         albedo = tx.albedo; roughness = tx.roughness; metallic = tx.metallic;
     }
     if (dot(d, normal) > 0.0f) {  // 15_module.py:985-988

@@ -89,7 +89,7 @@ k_shade(const SceneView sv, const RenderConsts rc, const PoolPtrs in, const floa
                     if (rc.accum_sq) atomicAdd(&accum_sq[p.pixel], make_float4(c.x * c.x, c.y * c.y, c.z * c.z, 1.0f));
                 }
             } else {
-                if (LEGACY) scatter_legacy(sv, p, h, rc.absorptivity, rc.seed);
+                if (LEGACY) scatter_legacy(sv, p, h, rc.absorptivity, rc.seed, sv.lut);
                 else scatter_v2(sv, p, h, rc.shading_model, rc.seed);
                 p.bounce += 1u;
                 alive = p.bounce < (uint32_t)rc.max_depth;  // paths over propagate_limit contribute nothing
@@ -199,7 +199,7 @@ k_paths(const SceneView sv, const RenderConsts rc, const PoolPtrs in, const Pool
                 }
                 alive = false;
             } else {  // shade / scatter
-                if (LEGACY) scatter_legacy(sv, p, h, rc.absorptivity, rc.seed);
+                if (LEGACY) scatter_legacy(sv, p, h, rc.absorptivity, rc.seed, sv.lut);
                 else scatter_v2(sv, p, h, rc.shading_model, rc.seed);
                 p.bounce += 1u;
                 alive = p.bounce < (uint32_t)rc.max_depth;
@@ -457,7 +457,14 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
                "PT_SHADE_V2_NORMALS needs a persistent kernel (mode 0, 3, 4 or 5)");
     PT_CUDA(cudaSetDevice(ctx->device));
 
-    const unsigned long long total = (unsigned long long)p->width * p->height * (unsigned long long)p->spp;
+    // reserved[4], [5]: a band of rows [row0, row1) instead of the whole frame (0, 0 = all rows) — the multi-GPU path
+    // renders band by band so that the reduce of one band overlaps the rendering of the next (persistent kernel only)
+    const bool banded = p->reserved[4] != 0 || p->reserved[5] != 0;
+    PT_REQUIRE(!banded || (p->reserved[4] >= 0 && p->reserved[4] < p->reserved[5] && p->reserved[5] <= p->height),
+               "reserved[4]/[5] (row band) must satisfy 0 <= row0 < row1 <= height");
+    PT_REQUIRE(!banded || mode == PT_MODE_PERSIST, "row bands need the persistent kernel (mode 0 or 3)");
+    const int row0 = banded ? p->reserved[4] : 0, row1 = banded ? p->reserved[5] : p->height;
+    const unsigned long long total = (unsigned long long)p->width * (unsigned long long)(row1 - row0) * (unsigned long long)p->spp;
     const size_t def_cap = mode == PT_MODE_SPLIT ? (size_t)1 << 22 : (size_t)1 << 21;
     size_t cap = p->pool_capacity > 0 ? (size_t)p->pool_capacity : def_cap;
     if (cap > total) cap = (size_t)total;
@@ -480,6 +487,7 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
     rc.stride_samples = (uint32_t)(cap / WH);
     rc.stride_pixels = (uint32_t)(cap % WH);
     rc.sample_end = (uint32_t)(p->spp_offset + p->spp);
+    rc.row0 = row0; rc.row1 = row1;
 
     cudaStream_t st = ctx->stream;
     const bool timing = (p->flags & PT_FLAG_TIMING) != 0;
@@ -489,13 +497,22 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
 
     int iterations = 0, launches = 0, rcode;
     size_t ev_idx = 0;
+#ifndef PT_EXPERIMENTAL
+    PT_REQUIRE(mode != PT_MODE_QUEUE && mode != PT_MODE_DUAL,
+               "render modes 4 (queue) and 5 (dual) are experimental kernel forms: rebuild with `make EXPERIMENTAL=1`");
+#endif
     if (mode == PT_MODE_QUEUE) {
+#ifdef PT_EXPERIMENTAL
         const int serve_min = p->reserved[3] > 0 ? p->reserved[3] : 24;
         if (timing) cudaEventRecord(get_event(ctx, ev_idx++), st);
         rcode = pt_render_queue(ctx, s, rc, legacy, count, (float4*)accum_dev, (float4*)accum_sq_dev, serve_min);
         if (timing) cudaEventRecord(get_event(ctx, ev_idx++), st);
         iterations = 1; launches = 1;
+#else
+        rcode = PT_ERR_INVALID;
+#endif
     } else if (mode == PT_MODE_DUAL) {
+#ifdef PT_EXPERIMENTAL
         // dual.cu: phases (miss / hit / regen) fire once shade_min lanes want exactly them
         const int shade_min = p->reserved[2] > 0 ? p->reserved[2] : 20;
         const int serve_min = p->reserved[3] > 0 ? p->reserved[3] : 8;
@@ -504,6 +521,9 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
                                p->reserved[1] == 3 ? 3 : 4);
         if (timing) cudaEventRecord(get_event(ctx, ev_idx++), st);
         iterations = 1; launches = 1;
+#else
+        rcode = PT_ERR_INVALID;
+#endif
     } else if (mode == PT_MODE_PERSIST) {
         // warp votes (persist.cu): a service (leaf tests, shading, refill) starts once serve_min more lanes wait
         // than after the previous one; finished lanes are shaded once shade_min of them have piled up
@@ -522,51 +542,71 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
                              p->reserved[1] > 0 ? p->reserved[1] : 32, &iterations, &launches, &ev_idx);
     if (rcode) return rcode;
 
-    unsigned long long last[CNT_WORDS];
-    PT_CUDA(cudaMemcpyAsync(last, ctx->counters, sizeof last, cudaMemcpyDeviceToHost, st));
+    // The counter block goes to pinned memory behind the kernel; nothing here waits for the GPU.  A caller that wants
+    // the statistics of THIS call passes `stats` (then the call ends with one stream synchronisation) or asks later with
+    // pt_render_stats() — the multi-GPU path renders with stats == NULL and lets the reduce follow on the same stream.
+    if (!ctx->stats_host) PT_CUDA(cudaMallocHost(&ctx->stats_host, CNT_WORDS * sizeof(unsigned long long)));
+    PT_CUDA(cudaMemcpyAsync(ctx->stats_host, ctx->counters, CNT_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     PT_CUDA(cudaEventRecord(ctx->ev_b, st));
-    PT_CUDA(cudaStreamSynchronize(st));
     PT_CUDA(cudaGetLastError());
-    if (stats) {
-        memset(stats, 0, sizeof *stats);
-        stats->paths = total;
-        stats->segments = last[CNT_SEGMENTS];
-        stats->nodes_visited = last[CNT_NODES];
-        stats->prims_tested = last[CNT_PRIMS];
-        cudaEventElapsedTime(&stats->ms_total, ctx->ev_a, ctx->ev_b);
-        stats->iterations = iterations;
-        stats->launches = launches;
-        if (mode == PT_MODE_SPLIT) {
-            stats->launches_extend = iterations;
-            stats->launches_shade = iterations;
-            if (timing) {
-                float e = 0, sh = 0;
-                for (size_t k = 0; k + 3 <= ev_idx; k += 3) {
-                    float a = 0, b = 0;
-                    cudaEventElapsedTime(&a, ctx->ev_pool[k], ctx->ev_pool[k + 1]);
-                    cudaEventElapsedTime(&b, ctx->ev_pool[k + 1], ctx->ev_pool[k + 2]);
-                    e += a; sh += b;
-                }
-                stats->ms_extend = e;
-                stats->ms_shade = sh;
+    ctx->last_paths = total;
+    ctx->last_mode = mode;
+    ctx->last_iterations = iterations;
+    ctx->last_launches = launches;
+    ctx->last_ev_idx = ev_idx;
+    ctx->last_timing = timing;
+    ctx->last_valid = true;
+    if (stats) return pt_render_stats(ctx, stats);
+    return PT_OK;
+}
+
+extern "C" int pt_render_stats(PtContext* ctx, PtStats* stats) {
+    PT_REQUIRE(ctx && stats, "null argument");
+    PT_REQUIRE(ctx->last_valid, "no pt_render call on this context yet");
+    PT_CUDA(cudaSetDevice(ctx->device));
+    PT_CUDA(cudaEventSynchronize(ctx->ev_b));
+    const unsigned long long* last = ctx->stats_host;
+    const int mode = ctx->last_mode, iterations = ctx->last_iterations, launches = ctx->last_launches;
+    const size_t ev_idx = ctx->last_ev_idx;
+    const bool timing = ctx->last_timing;
+    memset(stats, 0, sizeof *stats);
+    stats->paths = ctx->last_paths;
+    stats->segments = last[CNT_SEGMENTS];
+    stats->nodes_visited = last[CNT_NODES];
+    stats->prims_tested = last[CNT_PRIMS];
+    cudaEventElapsedTime(&stats->ms_total, ctx->ev_a, ctx->ev_b);
+    stats->iterations = iterations;
+    stats->launches = launches;
+    if (mode == PT_MODE_SPLIT) {
+        stats->launches_extend = iterations;
+        stats->launches_shade = iterations;
+        if (timing) {
+            float e = 0, sh = 0;
+            for (size_t k = 0; k + 3 <= ev_idx; k += 3) {
+                float a = 0, b = 0;
+                cudaEventElapsedTime(&a, ctx->ev_pool[k], ctx->ev_pool[k + 1]);
+                cudaEventElapsedTime(&b, ctx->ev_pool[k + 1], ctx->ev_pool[k + 2]);
+                e += a; sh += b;
             }
-        } else {  // fused: one kernel does both stages; its time is reported under ms_shade, launches under both
-            stats->launches_extend = 0;
-            stats->launches_shade = launches;
-            if (timing) {
-                float sh = 0;
-                for (size_t k = 0; k + 2 <= ev_idx; k += 2) {
-                    float a = 0;
-                    cudaEventElapsedTime(&a, ctx->ev_pool[k], ctx->ev_pool[k + 1]);
-                    sh += a;
-                }
-                stats->ms_shade = sh;
-            }
+            stats->ms_extend = e;
+            stats->ms_shade = sh;
         }
-        if (timing) stats->ms_other = stats->ms_total - stats->ms_extend - stats->ms_shade;
-        stats->reserved[0] = mode;
-        stats->reserved[3] = (int32_t)last[15];  // debug code of the queue kernel (0 unless built with -DQ_DEBUG)
+    } else {  // fused: one kernel does both stages; its time is reported under ms_shade, launches under both
+        stats->launches_extend = 0;
+        stats->launches_shade = launches;
+        if (timing) {
+            float sh = 0;
+            for (size_t k = 0; k + 2 <= ev_idx; k += 2) {
+                float a = 0;
+                cudaEventElapsedTime(&a, ctx->ev_pool[k], ctx->ev_pool[k + 1]);
+                sh += a;
+            }
+            stats->ms_shade = sh;
+        }
     }
+    if (timing) stats->ms_other = stats->ms_total - stats->ms_extend - stats->ms_shade;
+    stats->reserved[0] = mode;
+    stats->reserved[3] = (int32_t)last[15];  // debug code of the queue kernel (0 unless built with -DQ_DEBUG)
     return PT_OK;
 }
 

@@ -35,6 +35,7 @@ struct RenderConsts {
     // fused mode: static striding of path ids over the pool, id -> (sample, pixel) without division
     uint32_t stride_samples, stride_pixels;  // pool_cap = stride_samples * W*H + stride_pixels
     uint32_t sample_end;                     // spp_offset + spp
+    int row0, row1;                          // rows [row0, row1) of the image are rendered (persistent kernel; else 0, H)
 };
 
 struct PoolPtrs {

@@ -479,6 +479,7 @@ def lbvh_to_reference_tree(nodes16, global_prims, tri9, max_leave_objects=4, max
 # ---- world -------------------------------------------------------------------------------------------
 class World:
     """15_module.py:782-848."""
+    shading_model = _lib.PT_SHADE_LEGACY  # gen_secondary_rays (15_module.py:994-1013); read by render_distributed
 
     def __init__(self, texture_size=texture_size, environment_size=environment_size):
         self.spheres = []
@@ -672,25 +673,79 @@ class World:
 
 
 class LegacyRenderer:
-    """render(moved) + gamma_correction of 15_module.py:1016-1036 with the script's module constants as fields."""
+    """render(moved) + gamma_correction of 15_module.py:1016-1036 with the script's module constants as fields.
 
-    def __init__(self, world: World, camera: Camera, spp=32, propagate_limit=32, absorptivity=0.25, seed=1, ctx=None):
+    Under an initialised torch.distributed process group (one rank per GPU) every pass of `spp` samples is split
+    over the ranks (multigpu.render_split_reduce: disjoint sample ranges, scene replicated, accumulators summed onto
+    rank 0 over NCCL); rank 0 owns the progressive image and returns the frame, the other ranks return None.
+    distributed=False keeps a renderer local to its rank."""
+
+    def __init__(self, world: World, camera: Camera, spp=32, propagate_limit=32, absorptivity=0.25, seed=1, ctx=None,
+                 distributed=True, group=None, bands=1):
         from .render import Renderer, default_context
         self.ctx = ctx or default_context()
         self.world, self.camera = world, camera
         self.spp, self.propagate_limit, self.absorptivity, self.seed = int(spp), int(propagate_limit), float(absorptivity), seed
         self.renderer = Renderer(camera.resolution[0], camera.resolution[1], self.ctx)
         self.frame = None
+        self.group, self.bands = group, int(bands)
+        self.distributed = bool(distributed)
+        self._total = 0       # samples per pixel in the image (over all ranks)
+        self._partial = None  # ranks > 0: scratch accumulator of one pass
 
     @property
     def total_spp(self):
-        return self.renderer.spp_done
+        return self._total
 
-    def render(self, moved=True):
-        """Adds `spp` samples per pixel (progressive unless moved) and returns frame = (image/spp)^(1/2.2)."""
+    def _ranks(self):
+        if not self.distributed:
+            return 1, 0
+        from .multigpu import _dist_active
+        if not _dist_active(self.group):
+            return 1, 0
+        import torch.distributed as dist
+        return dist.get_world_size(self.group), dist.get_rank(self.group)
+
+    def render(self, moved=True, spp_offset=None):
+        """Adds `spp` samples per pixel (progressive unless moved) and returns frame = (image/spp)^(1/2.2).
+        spp_offset: first sample index of this pass (default: continue after the samples already in the image)."""
+        from .multigpu import render_split_reduce
+        ws, rank = self._ranks()
         if moved:
             self.renderer.clear()
-        self.renderer.render(self.world.device_scene(self.ctx), self.camera.to_struct(), self.spp, self.propagate_limit,
-                             _lib.PT_SHADE_LEGACY, self.seed, absorptivity=self.absorptivity)
-        self.frame = self.renderer.image(aces=False, gamma=2.2)
+            self._total = 0
+        first = self._total if spp_offset is None else int(spp_offset)
+        scene = self.world.device_scene(self.ctx)
+        if ws == 1:
+            self.renderer.render(scene, self.camera.to_struct(), self.spp, self.propagate_limit, _lib.PT_SHADE_LEGACY,
+                                 self.seed, spp_offset=first, absorptivity=self.absorptivity, want_stats=False)
+        else:
+            # the pass of every rank lands in a scratch accumulator that is summed onto rank 0 and added to its image
+            torch = self.renderer.torch
+            if self._partial is None:
+                from .render import Renderer
+                self._partial = Renderer(self.renderer.width, self.renderer.height, self.ctx)
+            self._partial.clear()
+            render_split_reduce(self._partial, scene, self.camera.to_struct(), self.spp, self.propagate_limit,
+                                _lib.PT_SHADE_LEGACY, self.seed, self.group, absorptivity=self.absorptivity,
+                                bands=self.bands, first_sample=first)
+            if rank == 0:
+                torch.add(self.renderer.accum, self._partial.accum, out=self.renderer.accum)
+        self._total += self.spp
+        self.renderer.spp_done = self._total
+        if rank != 0:
+            self.frame = None
+            return None
+        self.frame = self.renderer.image(aces=False, gamma=2.2, total_spp=self._total)
         return self.frame
+
+    def frames(self, camera_path, passes_per_pose=1):
+        """Frame streaming (the consumer of Camera.move_*/rotate that 12_free_view.py:553-579 / 15_module.py:403-421 feed
+        a ti.GUI with): for every pose of `camera_path` — a callable pose(camera) that moves the camera in place, or
+        None to keep it — the image restarts (render(moved=True)) and `passes_per_pose` progressive passes are yielded
+        as (pose index, pass index, frame).  The device scene is built once and reused for the whole stream."""
+        for k, pose in enumerate(camera_path):
+            if pose is not None:
+                pose(self.camera)
+            for j in range(int(passes_per_pose)):
+                yield k, j, self.render(moved=(j == 0))

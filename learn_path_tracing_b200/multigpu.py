@@ -3,9 +3,16 @@
 The reference has no multi-GPU path (it pins one device with CUDA_VISIBLE_DEVICES, 15_module.py:10).
 Here every rank (one process per GPU, torchrun) holds a replica of the scene and renders a disjoint
 range of sample indices for every pixel; the counter-based RNG is keyed on (seed, pixel, sample, bounce)
-so the union over ranks is exactly the set of paths a single GPU would trace.  The per-GPU float4
-accumulators are then summed onto rank 0 with one torch.distributed.reduce (NCCL over NVLink; gloo in
-the CPU tests) and rank 0 runs the fused divide-by-spp + tonemap kernel.
+so the union over ranks is exactly the set of paths a single GPU would trace.  The per-GPU accumulators are
+then summed onto rank 0 with torch.distributed.reduce (NCCL over NVLink; gloo in the CPU tests) and rank 0
+runs the fused divide-by-spp + tonemap kernel.
+
+Nothing on this path waits for the GPU on the host: pt_render is enqueued without statistics, the reduce follows on
+the same stream, and the only synchronisation is rank 0's read of the finished image.  With `bands` > 1 the frame is
+rendered in horizontal bands and the reduce of band k runs on a side stream while band k + 1 renders, so only the
+last band's reduce is exposed (strong scaling of short frames: 8_refract at 32 spp per GPU is a 3.7 ms render).
+Works for the v2 sphere worlds and for the legacy mesh worlds (the shading model follows the world type;
+legacy/PT_in_one_weekend/15_module.py:1022-1036 is the loop it replaces).
 """
 from __future__ import annotations
 
@@ -20,47 +27,107 @@ def split_samples(spp: int, world_size: int, rank: int) -> tuple[int, int]:
     return offset, count
 
 
-def reduce_accumulators(accum, dst: int = 0, group=None):
-    """Sum the per-rank accumulators onto `dst` (in place).  No-op without an initialised process group."""
+def _dist_active(group=None) -> bool:
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+def reduce_accumulators(accum, dst: int = 0, group=None, channels: int = 4):
+    """Sum the per-rank accumulators ([H*W,4] float: r, g, b, contributing paths) onto `dst`, in place.  channels=3
+    ships only the radiance (the path count is a diagnostic): 25 % fewer bytes over NVLink at the price of one
+    packing copy on every rank.  No-op without an initialised process group."""
+    import torch.distributed as dist
+    if not _dist_active(group):
+        return accum
+    if channels >= accum.shape[-1]:
         dist.reduce(accum, dst=dst, op=dist.ReduceOp.SUM, group=group)
+        return accum
+    rgb = accum[:, :channels].contiguous()
+    dist.reduce(rgb, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    if dist.get_rank(group) == dst:
+        accum[:, :channels].copy_(rgb)
     return accum
 
 
-def render_distributed(world, camera, spp: int = 8192, propagate_limit: int = 32, seed: int = 1, bsdf=None,
-                       ctx=None, group=None, render_accum=None, postprocess=True):
-    """render(world, camera) across all ranks of the process group.
+def world_shading_model(world, bsdf=None) -> int:
+    """Legacy (mesh / textured-sphere) worlds shade with gen_secondary_rays (15_module.py:994-1013); v2 worlds with the
+    BSDF class the script names (default Metal/Dielectric)."""
+    if getattr(world, "shading_model", None) is not None and bsdf is None:
+        return int(world.shading_model)
+    return int(getattr(bsdf, "shading_model", _lib.PT_SHADE_V2))
 
-    Returns the image ([W,H,3] float32, tonemapped when `postprocess`) on rank 0 and None elsewhere.
+
+def render_split_reduce(renderer, scene, cam_struct, spp: int, max_depth: int, model: int, seed: int, group=None,
+                        absorptivity: float = 0.25, bands: int = 1, channels: int = 3, flags: int = 0,
+                        first_sample: int = 0, **render_kw):
+    """This rank's share of `spp` samples into renderer.accum, then the sum over ranks onto rank 0 — all enqueued, nothing
+    awaited.  Returns (sample offset, sample count) of this rank."""
+    import torch
+    import torch.distributed as dist
+    active = _dist_active(group)
+    ws = dist.get_world_size(group) if active else 1
+    rank = dist.get_rank(group) if active else 0
+    offset, count = split_samples(spp, ws, rank)
+    offset += int(first_sample)  # progressive passes: this pass covers sample indices [first_sample, first_sample + spp)
+    H, W = renderer.height, renderer.width
+    bands = max(1, min(int(bands), H)) if active else 1
+    if bands == 1:
+        renderer.render(scene, cam_struct, count, max_depth, model, seed, spp_offset=offset, absorptivity=absorptivity,
+                        flags=flags, want_stats=False, **render_kw)
+        reduce_accumulators(renderer.accum, 0, group, channels)
+        return offset, count
+    main = torch.cuda.current_stream()
+    side = renderer.side_stream()
+    edges = [H * b // bands for b in range(bands + 1)]
+    rows = renderer.accum.view(H, W, 4)
+    for b in range(bands):
+        y0, y1 = edges[b], edges[b + 1]
+        renderer.render(scene, cam_struct, count, max_depth, model, seed, spp_offset=offset, absorptivity=absorptivity,
+                        flags=flags, want_stats=False, rows=(y0, y1), count_samples=(b == bands - 1), **render_kw)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(side):  # band b travels while band b + 1 renders
+            side.wait_event(ev)
+            dist.reduce(rows[y0:y1], dst=0, op=dist.ReduceOp.SUM, group=group)  # whole rows are contiguous: no packing
+    main.wait_stream(side)
+    return offset, count
+
+
+def render_distributed(world, camera, spp: int = 8192, propagate_limit: int = 32, seed: int = 1, bsdf=None,
+                       ctx=None, group=None, render_accum=None, postprocess=True, absorptivity: float = 0.25,
+                       bands: int = 1, channels: int = 3):
+    """render(world, camera) across all ranks of the process group (v2 World or legacy World).
+
+    Returns the image ([W,H,3] float32; v2: ACES + gamma, legacy: gamma only, as the two reference scripts do; the
+    linear mean when not `postprocess`) on rank 0 and None elsewhere.
     `render_accum(offset, count) -> tensor[H*W,4]` can replace the CUDA renderer (the gloo/CPU tests inject
     the oracle there); by default it is Renderer.render on this rank's GPU.
     """
     import torch.distributed as dist
-    ws = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
-    offset, count = split_samples(spp, ws, rank)
+    active = _dist_active(group)
+    ws = dist.get_world_size(group) if active else 1
+    rank = dist.get_rank(group) if active else 0
     w, h = camera.resolution
-    renderer = None
+    model = world_shading_model(world, bsdf)
+    legacy = model == _lib.PT_SHADE_LEGACY
     if render_accum is None:
         from .render import Renderer, default_context
         ctx = ctx or default_context()
         renderer = Renderer(w, h, ctx)
-        model = getattr(bsdf, "shading_model", _lib.PT_SHADE_V2)
-        renderer.render(world.device_scene(ctx), camera.to_struct(), count, propagate_limit, model, seed,
-                        spp_offset=offset)
-        accum = renderer.accum
-    else:
-        accum = render_accum(offset, count)
-    reduce_accumulators(accum, 0, group)
+        render_split_reduce(renderer, world.device_scene(ctx), camera.to_struct(), spp, propagate_limit, model, seed, group,
+                            absorptivity=absorptivity, bands=bands, channels=channels)
+        if rank != 0:
+            return None
+        if postprocess:
+            return renderer.image(aces=not legacy, gamma=2.2, total_spp=spp)
+        return renderer.ctx.download_accum(renderer.accum.data_ptr(), w, h) / float(spp)
+    offset, count = split_samples(spp, ws, rank)
+    accum = render_accum(offset, count)
+    reduce_accumulators(accum, 0, group, channels)
     if rank != 0:
         return None
-    if renderer is not None:
-        if postprocess:
-            return renderer.image(aces=True, gamma=2.2, total_spp=spp)
-        return renderer.ctx.download_accum(accum.data_ptr(), w, h) / float(spp)
     img = accum[:, :3].reshape(h, w, 3).permute(1, 0, 2).contiguous().cpu().numpy() / float(spp)
     if postprocess:
         from .postprocessing import ACES_tonemapping, gamma_correction
-        img = gamma_correction(ACES_tonemapping(img), 2.2)
+        img = gamma_correction(img if legacy else ACES_tonemapping(img), 2.2)
     return img

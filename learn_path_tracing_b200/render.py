@@ -51,8 +51,13 @@ class Renderer:
     def render(self, scene: _lib.Scene, cam: _lib.PtCamera, spp: int, max_depth: int,
                shading_model: int = _lib.PT_SHADE_V2, seed: int = 1, spp_offset: int | None = None,
                absorptivity: float = 0.25, flags: int = 0, pool_capacity: int = 0, mode: int = 0,
-               segments_per_launch: int = 0, shade_min: int = 0, serve_min: int = 0) -> _lib.PtStats:
-        """Adds `spp` more samples per pixel into the accumulators (progressive, legacy render(moved=False))."""
+               segments_per_launch: int = 0, shade_min: int = 0, serve_min: int = 0,
+               want_stats: bool = True, rows: tuple[int, int] | None = None,
+               count_samples: bool = True) -> _lib.PtStats | None:
+        """Adds `spp` more samples per pixel into the accumulators (progressive, legacy render(moved=False)).
+        want_stats=False returns None without waiting for the GPU (Renderer.stats() fetches them later).
+        rows=(y0, y1) renders only that band of image rows (persistent kernel); count_samples=False leaves spp_done alone
+        (all bands but the last of one banded pass)."""
         p = _lib.PtRenderParams()
         p.width, p.height = self.width, self.height
         p.spp = int(spp)
@@ -67,12 +72,27 @@ class Renderer:
         p.reserved[2] = int(shade_min)            # persistent: finished lanes that trigger shading/refill (0 = default)
         p.reserved[3] = int(serve_min)            # persistent: waiting lanes that trigger a service (0 = default)
         p.reserved[1] = int(segments_per_launch)  # fused: ray segments per path slot per launch (0 = 32)
+        if rows is not None:
+            p.reserved[4], p.reserved[5] = int(rows[0]), int(rows[1])
         self.ctx.set_stream(self.torch.cuda.current_stream().cuda_stream)
         st = self.ctx.render(scene, cam, p, self.accum.data_ptr(),
-                             self.accum_sq.data_ptr() if self.accum_sq is not None else None)
-        self.spp_done += int(spp)
+                             self.accum_sq.data_ptr() if self.accum_sq is not None else None, want_stats=want_stats)
+        if count_samples:
+            self.spp_done += int(spp)
         self.last_stats = st
         return st
+
+    def side_stream(self):
+        """A second CUDA stream of this renderer (reduce of one row band beside the rendering of the next)."""
+        if getattr(self, "_side", None) is None:
+            self._side = self.torch.cuda.Stream(device=self.accum.device)
+        return self._side
+
+    def stats(self) -> _lib.PtStats:
+        """Statistics of the last render() (fetched now if that call did not wait for them)."""
+        if self.last_stats is None:
+            self.last_stats = self.ctx.render_stats()
+        return self.last_stats
 
     def mean(self) -> np.ndarray:
         """Linear radiance estimate, Taichi field layout [W,H,3]."""

@@ -69,7 +69,7 @@ def test_config1_kernel_forms_and_sample_split_agree_at_full_size(ctx):
     world, cam = scenes.scene_8_refract((W, H))
     sc = world.device_scene(ctx)
     ref = None
-    for mode in (L.PT_MODE_PERSIST, L.PT_MODE_FUSED, L.PT_MODE_SPLIT, L.PT_MODE_DUAL):
+    for mode in [L.PT_MODE_PERSIST, L.PT_MODE_FUSED, L.PT_MODE_SPLIT] + ([L.PT_MODE_DUAL] if L._lib.has_experimental() else []):
         r = L.Renderer(W, H, ctx)
         st = r.render(sc, cam.to_struct(), 32, DEPTH, seed=9, mode=mode)
         m = r.mean()
@@ -110,7 +110,7 @@ def test_config2_yoimiya_1080p_512spp_properties(ctx):
     sb = b.render(sc, cam.to_struct(), 16, DEPTH, L.PT_SHADE_LEGACY, seed=3, mode=L.PT_MODE_SPLIT)
     assert abs(int(sa.segments) - int(sb.segments)) <= 2e-4 * sb.segments
     assert np.allclose(a.mean(), b.mean(), rtol=2e-3, atol=2e-4)
-    for bps in (3, 4):   # the two-records-per-lane kernel at 3 and 4 blocks per SM
+    for bps in ((3, 4) if L._lib.has_experimental() else ()):   # the two-records-per-lane kernel at 3 and 4 blocks per SM
         c = L.Renderer(W, H, ctx)
         sc_ = c.render(sc, cam.to_struct(), 16, DEPTH, L.PT_SHADE_LEGACY, seed=3, mode=L.PT_MODE_DUAL, segments_per_launch=bps)
         assert abs(int(sc_.segments) - int(sb.segments)) <= 2e-4 * sb.segments

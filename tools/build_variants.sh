@@ -8,7 +8,7 @@ while [ $# -ge 2 ]; do
   name=$1; flags=$2; shift 2
   tmp=/tmp/ptvar_$name; rm -rf $tmp; mkdir -p $tmp/learn_path_tracing_b200 $tmp/include
   cp -r $root/learn_path_tracing_b200/csrc $tmp/learn_path_tracing_b200/csrc; cp $root/include/*.h $tmp/include/
-  rm -f $tmp/learn_path_tracing_b200/csrc/*.o
+  rm -rf $tmp/learn_path_tracing_b200/csrc/*.o $tmp/learn_path_tracing_b200/csrc/obj $tmp/learn_path_tracing_b200/csrc/obj_exp
   make -s -C $tmp/learn_path_tracing_b200/csrc -j8 EXTRA="$flags" OUT=$root/learn_path_tracing_b200/variants/libb200pt_$name.so &
 done
 wait
