@@ -369,6 +369,7 @@ def measure_render(D, name, steps, warmup, args, cpu_seconds=0.0):
     frac = achieved / peak
     roof = {"bound": "hbm", "kernel": KERNEL_OF.get(name, "k_paths_persist"), "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": frac, "traffic": nc.get("dram_bytes_per_launch") if nc else None, "traffic_source": nc_src,
+            "traffic_captured_as": nc.get("captured_as") if nc else None,
             "peak_kind": peak_kind, "avg_launch_ms": ms_kernel, "algorithmic_bytes_per_launch": bytes_launch,
             "algorithmic_bytes": "SURVEY 8d: 160 B per ray segment + 24 B per path = what a split wavefront moves through HBM. "
                                  "NOMINAL for this kernel: a path lives in registers from its camera ray to its last segment, so the "
@@ -463,6 +464,7 @@ def measure_intersect(D, name, steps, warmup, args):
     nc, nc_src = ncu_counters(name)
     roof = {"bound": "hbm", "kernel": KERNEL_OF.get(name, "k_trace_persist"), "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": nc.get("dram_bytes_per_launch") if nc else None, "traffic_source": nc_src,
+            "traffic_captured_as": nc.get("captured_as") if nc else None,
             "peak_kind": peak_kind, "avg_launch_ms": ms_kernel,
             "step_ms": {"ray_sort": st_plain.ms_other, "traversal": st_plain.ms_extend, "step": t_local / steps},
             "algorithmic_bytes_per_launch": bytes_per_ray * n_local,

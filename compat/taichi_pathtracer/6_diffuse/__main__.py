@@ -1,8 +1,9 @@
-"""Drop-in for taichi_pathtracer/6_diffuse/__main__.py: run as `python compat/taichi_pathtracer/6_diffuse` from the repo root."""
+"""python compat/taichi_pathtracer/6_diffuse — drop-in for the reference's taichi_pathtracer/6_diffuse (same idiom through the shim:
+compat/taichi_pathtracer/_shim_driver.py; the reference's own script also runs unmodified with PYTHONPATH=.../_shim)."""
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from _driver import main  # noqa: E402
+from _shim_driver import main  # noqa: E402
 
 main("6_diffuse")

@@ -1,8 +1,9 @@
-"""Drop-in for taichi_pathtracer/7_reflect/__main__.py: run as `python compat/taichi_pathtracer/7_reflect` from the repo root."""
+"""python compat/taichi_pathtracer/7_reflect — drop-in for the reference's taichi_pathtracer/7_reflect (same idiom through the shim:
+compat/taichi_pathtracer/_shim_driver.py; the reference's own script also runs unmodified with PYTHONPATH=.../_shim)."""
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from _driver import main  # noqa: E402
+from _shim_driver import main  # noqa: E402
 
 main("7_reflect")

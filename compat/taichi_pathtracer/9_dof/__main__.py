@@ -1,8 +1,9 @@
-"""Drop-in for taichi_pathtracer/9_dof/__main__.py: run as `python compat/taichi_pathtracer/9_dof` from the repo root."""
+"""python compat/taichi_pathtracer/9_dof — drop-in for the reference's taichi_pathtracer/9_dof (same idiom through the shim:
+compat/taichi_pathtracer/_shim_driver.py; the reference's own script also runs unmodified with PYTHONPATH=.../_shim)."""
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from _driver import main  # noqa: E402
+from _shim_driver import main  # noqa: E402
 
 main("9_dof")

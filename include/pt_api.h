@@ -56,12 +56,22 @@ extern "C" {
 #define PT_SHADE_V2_NORMALS 3   /* taichi_pathtracer stages 4-5: colour = 0.5 (normal + 1), no bounce (5_anti_aliasing/__main__.py:19-28);
                                    persistent kernel only                                                      */
 
+#define PT_SHADE_LEGACY_STAGE7 4 /* legacy/PT_in_one_weekend/7_reflect.py:187-209 (the untextured ancestor of gen_secondary_rays: the
+                                   same cal_reflectivity_metal / _dielectirc, sample_in_sphere, sample_reflect, sample_diffuse as
+                                   15_module.py:281-334): v2-style spheres with constant materials, `metallic` a switch, diffuse
+                                   throughput albedo * params.absorptivity, reflection lobe scaled by k = -d.n, hits accepted for
+                                   t > 1e-3 (near root only), rays leave from the hit point; sky gradient.  Persistent kernel only */
+#define PT_SHADE_LEGACY_STAGE6 5 /* legacy/PT_in_one_weekend/6_diffuse.py:160-170: every hit is sample_diffuse with throughput
+                                   params.absorptivity (0.5) * albedo; same hit rule.  Persistent kernel only                    */
+
 /* PtRenderParams.flags */
 #define PT_FLAG_ACCUM_SQ 1      /* also accumulate per-pixel sum of squares (needs accum_sq != NULL)   */
 #define PT_FLAG_TIMING 2        /* record CUDA events around every kernel launch (fills PtStats.ms_*)  */
 #define PT_FLAG_COUNTERS 4      /* count BVH nodes visited / primitives tested (slower)                */
 #define PT_FLAG_PIXEL_GRID 64   /* stages 2-4 camera (2_camera_and_ray/camera.py:67): the ray of pixel (i, j) goes through
                                    the lattice point (i/(W-1), j/(H-1)) of the view rectangle, no jitter (W, H >= 2)    */
+#define PT_FLAG_RAYS_FAST 256   /* pt_generate_rays_ex only: legacy Camera.get_rays_fast (15_module.py:423-436): the ray of pixel
+                                   (i, j) goes through (i/W, j/H) of the view rectangle, pinhole, focal length 1, no jitter */
 /* pt_trace_batch_device flags */
 #define PT_FLAG_NO_SORT 8       /* keep the batch order (default: batches >= 65536 rays are traced in an
                                    entry-point/direction Morton order; results always land in batch order) */
@@ -200,6 +210,9 @@ int pt_scene_triangles_download(const PtScene* s, float* tris, int64_t n);
  * d.xyz, tmax on the HOST (testing aid; the render generates rays on the fly).                  */
 int pt_generate_rays(PtContext* ctx, const PtCamera* cam, int width, int height, int sample, uint32_t seed,
                      float* rays_host);
+/* same with flags: PT_FLAG_PIXEL_GRID (stages 2-4 lattice) or PT_FLAG_RAYS_FAST (legacy Camera.get_rays_fast) */
+int pt_generate_rays_ex(PtContext* ctx, const PtCamera* cam, int width, int height, int sample, uint32_t seed,
+                        int flags, float* rays_host);
 
 /* closest hit for a fixed ray batch.  rays[n][8] = o.xyz, tmin, d.xyz, tmax.
  * prim_id[n] = -1 on miss; t[n] = -1 on miss; uv may be NULL.                                   */

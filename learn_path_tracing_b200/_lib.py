@@ -19,12 +19,15 @@ PT_SHADE_V2 = 0
 PT_SHADE_V2_DIFFUSE = 1
 PT_SHADE_LEGACY = 2
 PT_SHADE_V2_NORMALS = 3
+PT_SHADE_LEGACY_STAGE7 = 4  # legacy/PT_in_one_weekend/7_reflect.py: untextured ancestor of gen_secondary_rays
+PT_SHADE_LEGACY_STAGE6 = 5  # legacy/PT_in_one_weekend/6_diffuse.py: diffuse only, throughput 0.5 * albedo
 
 PT_FLAG_ACCUM_SQ = 1
 PT_FLAG_TIMING = 2
 PT_FLAG_COUNTERS = 4
 PT_FLAG_TRACE_WIDE = 128  # `make EXPERIMENTAL=1` builds only: 4-wide traversal (scene built with PT_WIDE=1); measured slower
 PT_FLAG_WIDE = PT_FLAG_TRACE_WIDE  # the same bit in PtRenderParams.flags (persistent mode)
+PT_FLAG_RAYS_FAST = 256  # generate_rays: legacy Camera.get_rays_fast lattice (i/W, pinhole)
 PT_FLAG_PIXEL_GRID = 64  # stages 2-4 camera: lattice rays i/(W-1), j/(H-1), no jitter
 
 PT_MODE_AUTO = 0
@@ -83,7 +86,7 @@ API_SYMBOLS = [
     "pt_scene_bvh_download", "pt_scene_triangles_download", "pt_generate_rays", "pt_trace_batch",
     "pt_trace_batch_device", "pt_random_rays_device", "pt_render", "pt_render_host", "pt_postprocess",
     "pt_postprocess_host", "pt_download_accum", "pt_measure_fp32_peak", "pt_last_error", "pt_version",
-    "pt_render_stats", "pt_build_info",
+    "pt_render_stats", "pt_build_info", "pt_generate_rays_ex",
 ]
 
 
@@ -144,6 +147,7 @@ def load():
         "pt_version": (i32, []),
         "pt_render_stats": (i32, [vp, P(PtStats)]),
         "pt_build_info": (C.c_char_p, []),
+        "pt_generate_rays_ex": (i32, [vp, P(PtCamera), i32, i32, i32, u32, i32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
@@ -203,9 +207,9 @@ class Context:
             pass
 
     # ---- hot-path calls -------------------------------------------------------------------
-    def generate_rays(self, cam: PtCamera, width: int, height: int, sample: int, seed: int) -> np.ndarray:
+    def generate_rays(self, cam: PtCamera, width: int, height: int, sample: int, seed: int, flags: int = 0) -> np.ndarray:
         rays = np.empty((height * width, 8), np.float32)
-        check(self.lib.pt_generate_rays(self.handle, C.byref(cam), width, height, sample, seed, _fptr(rays)))
+        check(self.lib.pt_generate_rays_ex(self.handle, C.byref(cam), width, height, sample, seed, int(flags), _fptr(rays)))
         return rays
 
     def trace_batch(self, scene: "Scene", rays: np.ndarray, counters: bool = False, out=None):

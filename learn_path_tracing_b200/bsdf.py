@@ -25,3 +25,14 @@ class DielectricBSDF:
 class NormalColor:
     """Stages 4-5 `ray_color`: 0.5 (normal + 1) on a hit, sky otherwise, no bounce — 5_anti_aliasing/__main__.py:19-28."""
     shading_model = _lib.PT_SHADE_V2_NORMALS
+
+
+class LegacyStage7BSDF:
+    """legacy/PT_in_one_weekend/7_reflect.py:187-209: cal_reflectivity_metal / _dielectirc, sample_reflect (lobe scaled by
+    k = -d.n), sample_diffuse with throughput albedo * absorptivity — the untextured form of 15_module.py:281-334,994-1013."""
+    shading_model = _lib.PT_SHADE_LEGACY_STAGE7
+
+
+class LegacyStage6BSDF:
+    """legacy/PT_in_one_weekend/6_diffuse.py:160-170: every hit scatters with sample_diffuse, l *= 0.5 * albedo."""
+    shading_model = _lib.PT_SHADE_LEGACY_STAGE6

@@ -52,10 +52,16 @@
 #ifndef PT_SSTACK_TRACE
 #define PT_SSTACK_TRACE 16
 #endif
-template <bool LEGACY, bool COUNT, bool WIDE = false>
+// KIND: 0 = v2 (taichi_pathtracer BSDFs), 1 = legacy textured meshes / spheres, 2 = legacy tutorial stages 6 / 7
+// (untextured spheres, shade.cuh:scatter_legacy_stage) — its own instantiation, the two hot kernels do not carry it.
+#define PT_KIND_V2 0
+#define PT_KIND_LEGACY 1
+#define PT_KIND_STAGE 2
+template <int KIND, bool COUNT, bool WIDE = false>
 __global__ void __launch_bounds__(PT_BLOCK, 4)
 k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* __restrict__ counters,
                 float4* __restrict__ accum, float4* __restrict__ accum_sq, int shade_min, int serve_min) {
+    constexpr bool LEGACY = KIND == PT_KIND_LEGACY;
     constexpr int NS = WIDE ? 0 : PT_SSTACK_RENDER;
     __shared__ int s_stack[NS ? NS : 1][PT_BLOCK];
     int lstack[(WIDE ? PT_STACK_WIDE : PT_STACK) - NS];
@@ -129,6 +135,7 @@ k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* _
                 } else {
                     T.h.t = T.best;
                     if (LEGACY) scatter_legacy(sv, p, T.h, rc.absorptivity, rc.seed, lut);
+                    else if (KIND == PT_KIND_STAGE) scatter_legacy_stage(sv, p, T.h, rc.shading_model, rc.absorptivity, rc.seed);
                     else scatter_v2(sv, p, T.h, rc.shading_model, rc.seed);
                     p.bounce += 1u;
                     st = p.bounce < (uint32_t)rc.max_depth ? ST_NEW : ST_IDLE;  // over propagate_limit: contributes nothing
@@ -425,16 +432,16 @@ int pt_trace_persist(PtContext* ctx, const PtScene* s, const float4* rays, long 
     return PT_OK;
 }
 
-template <bool LEGACY, bool COUNT, bool WIDE>
+template <int KIND, bool COUNT, bool WIDE>
 static int launch_persist(PtContext* ctx, const PtScene* s, const RenderConsts& rc, float4* accum, float4* accum_sq, int shade_min,
                           int serve_min) {
     int blocks = 0;
-    int rcb = resident_blocks(ctx, k_paths_persist<LEGACY, COUNT, WIDE>, &blocks);
+    int rcb = resident_blocks(ctx, k_paths_persist<KIND, COUNT, WIDE>, &blocks);
     if (rcb) return rcb;
     const unsigned long long need = (rc.total_paths + PT_BLOCK - 1) / PT_BLOCK;
     if ((unsigned long long)blocks > need) blocks = (int)need;
     if (blocks < 1) return PT_OK;
-    k_paths_persist<LEGACY, COUNT, WIDE><<<blocks, PT_BLOCK, 0, ctx->stream>>>(s->view, rc, ctx->counters, accum, accum_sq, shade_min, serve_min);
+    k_paths_persist<KIND, COUNT, WIDE><<<blocks, PT_BLOCK, 0, ctx->stream>>>(s->view, rc, ctx->counters, accum, accum_sq, shade_min, serve_min);
     PT_CUDA(cudaGetLastError());
     return PT_OK;
 }
@@ -443,16 +450,19 @@ int pt_render_persist(PtContext* ctx, const PtScene* s, const RenderConsts& rc, 
                       float4* accum_sq, int shade_min, int serve_min, bool wide) {
 #ifdef PT_EXPERIMENTAL
     if (wide) {  // experimental: the node phase walks the 4-wide copy of the tree
-        if (legacy) return count ? launch_persist<true, true, true>(ctx, s, rc, accum, accum_sq, shade_min, serve_min)
-                                 : launch_persist<true, false, true>(ctx, s, rc, accum, accum_sq, shade_min, serve_min);
-        return count ? launch_persist<false, true, true>(ctx, s, rc, accum, accum_sq, shade_min, serve_min)
-                     : launch_persist<false, false, true>(ctx, s, rc, accum, accum_sq, shade_min, serve_min);
+        if (legacy) return count ? launch_persist<PT_KIND_LEGACY, true, true>(ctx, s, rc, accum, accum_sq, shade_min, serve_min)
+                                 : launch_persist<PT_KIND_LEGACY, false, true>(ctx, s, rc, accum, accum_sq, shade_min, serve_min);
+        return count ? launch_persist<PT_KIND_V2, true, true>(ctx, s, rc, accum, accum_sq, shade_min, serve_min)
+                     : launch_persist<PT_KIND_V2, false, true>(ctx, s, rc, accum, accum_sq, shade_min, serve_min);
     }
 #else
     PT_REQUIRE(!wide, "the 4-wide walk is an experimental kernel form: rebuild with `make EXPERIMENTAL=1`");
 #endif
-    if (legacy) return count ? launch_persist<true, true, false>(ctx, s, rc, accum, accum_sq, shade_min, serve_min)
-                             : launch_persist<true, false, false>(ctx, s, rc, accum, accum_sq, shade_min, serve_min);
-    return count ? launch_persist<false, true, false>(ctx, s, rc, accum, accum_sq, shade_min, serve_min)
-                 : launch_persist<false, false, false>(ctx, s, rc, accum, accum_sq, shade_min, serve_min);
+    if (rc.shading_model == PT_SHADE_LEGACY_STAGE6 || rc.shading_model == PT_SHADE_LEGACY_STAGE7)
+        return count ? launch_persist<PT_KIND_STAGE, true, false>(ctx, s, rc, accum, accum_sq, shade_min, serve_min)
+                     : launch_persist<PT_KIND_STAGE, false, false>(ctx, s, rc, accum, accum_sq, shade_min, serve_min);
+    if (legacy) return count ? launch_persist<PT_KIND_LEGACY, true, false>(ctx, s, rc, accum, accum_sq, shade_min, serve_min)
+                             : launch_persist<PT_KIND_LEGACY, false, false>(ctx, s, rc, accum, accum_sq, shade_min, serve_min);
+    return count ? launch_persist<PT_KIND_V2, true, false>(ctx, s, rc, accum, accum_sq, shade_min, serve_min)
+                 : launch_persist<PT_KIND_V2, false, false>(ctx, s, rc, accum, accum_sq, shade_min, serve_min);
 }

@@ -286,6 +286,49 @@ PT_DEV void scatter_legacy(const SceneView& sv, PathState& p, const Hit& h, floa
     p.o = point + (2.0f * PT_EPS) * normal;  // :1013
 }
 
+// ---- legacy tutorial stages 6 / 7 (untextured) ---------------------------------------------------
+// legacy/PT_in_one_weekend/7_reflect.py:187-209 (propagate_once) with :49-96 (cal_reflectivity_*, sample_*) and
+// 6_diffuse.py:160-170.  These are the functions 15_module.py:281-334 still uses, on constant-material spheres under
+// the sky gradient — the only form of the legacy scattering model whose converged renders are in the reference
+// checkout (legacy/PT_in_one_weekend/{6_diffuse,7_reflect}.png).  No back-face flip (a sphere is only ever met from
+// outside: World.hit keeps the near root and t > 1e-3), no origin offset.
+PT_DEV void scatter_legacy_stage(const SceneView& sv, PathState& p, const Hit& h, int shading_model, float absorptivity,
+                                 uint32_t seed) {
+    const float4 cr = __ldg(&sv.sph_cr[h.prim]);
+    const float4 m0 = __ldg(&sv.sph_mat[2 * h.prim]);
+    const float4 m1 = __ldg(&sv.sph_mat[2 * h.prim + 1]);
+    const float3 albedo = f3(m0), d = p.d;
+    const float3 point = p.o + h.t * d;
+    const float3 normal = normalize(point - f3(cr));
+    const float4 u = rng4(p.pixel, p.sample, 1u + 2u * p.bounce, seed);
+    p.o = point;
+    if (shading_model == PT_SHADE_LEGACY_STAGE6) {  // 6_diffuse.py:165-167
+        p.l = absorptivity * p.l * albedo;
+        p.d = normalize(normal + sample_at_sphere(u.z, u.w));
+        return;
+    }
+    const float w = pow5(1.0f + dot(normal, d));
+    bool mirror;
+    if (__float_as_int(m1.x) != 0) {  // metallic: cal_reflectivity_metal, 7_reflect.py:49-53,191-194
+        p.l = p.l * f3(albedo.x + (1.0f - albedo.x) * w, albedo.y + (1.0f - albedo.y) * w, albedo.z + (1.0f - albedo.z) * w);
+        mirror = true;
+    } else {  // cal_reflectivity_dielectirc :56-60, the coin :197
+        float f0 = (m1.y - 1.0f) / (m1.y + 1.0f);
+        f0 *= f0;
+        mirror = !(u.y > f0 + (1.0f - f0) * w);
+        if (!mirror) {  // :198-199
+            p.l = p.l * (albedo * absorptivity);
+            p.d = normalize(normal + sample_at_sphere(u.z, u.w));
+        }
+    }
+    if (mirror) {  // sample_reflect :91-96: the lobe shrinks with k = -d.n (15_module.py:329-334 dropped that factor)
+        const float4 u2 = rng4(p.pixel, p.sample, 2u + 2u * p.bounce, seed);
+        const float3 s = sample_in_sphere(u.z, u.w, u2.x);
+        const float k = -dot(d, normal);
+        p.d = normalize(d + (2.0f * k) * normal + (k * m0.w) * s);
+    }
+}
+
 // ---- camera: Camera.get_rays (camera.py:71-93, 15_module.py:438-453) ---------------------------
 struct CameraDev {
     float3 pos, front, right, up;

@@ -288,7 +288,10 @@ __global__ void k_random_rays(float4* rays, long long n, uint32_t seed) {
 }
 
 // ------------------------------------------------------------------------------------------------
-static CameraDev make_camera(const PtCamera* c, int W, int H, bool grid = false) {
+// lattice: 0 = jittered pixel samples (Camera.get_rays), 1 = PT_FLAG_PIXEL_GRID (i/(W-1), stages 2-4),
+// 2 = PT_FLAG_RAYS_FAST (legacy Camera.get_rays_fast, 15_module.py:423-436: i/W, pinhole, focal length 1)
+static CameraDev make_camera(const PtCamera* c, int W, int H, int lattice = 0) {
+    const bool grid = lattice == 1;
     CameraDev d;
     d.pos = make_float3(c->pos[0], c->pos[1], c->pos[2]);
     d.front = make_float3(c->front[0], c->front[1], c->front[2]);
@@ -297,7 +300,8 @@ static CameraDev make_camera(const PtCamera* c, int W, int H, bool grid = false)
     d.view_w = c->view_w; d.view_h = c->view_h;
     d.focal = c->focal_length; d.aperture = c->aperture;
     d.inv_w = 1.0f / (float)(grid ? W - 1 : W); d.inv_h = 1.0f / (float)(grid ? H - 1 : H);
-    d.jitter = grid ? 0.0f : 1.0f;
+    d.jitter = lattice ? 0.0f : 1.0f;
+    if (lattice == 2) { d.focal = 1.0f; d.aperture = 0.0f; }
     return d;
 }
 
@@ -439,7 +443,7 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
     PT_REQUIRE(p->max_depth > 0 && p->max_depth < 256, "max_depth must be in [1,255]");
     PT_REQUIRE((long long)p->spp_offset + p->spp <= (1 << 24), "sample index must stay below 2^24");
     PT_REQUIRE((long long)p->width * p->height < (1ll << 31), "image too large");
-    PT_REQUIRE(p->shading_model >= 0 && p->shading_model <= 3, "unknown shading model");
+    PT_REQUIRE(p->shading_model >= 0 && p->shading_model <= 5, "unknown shading model");
     const bool legacy = p->shading_model == PT_SHADE_LEGACY;
     PT_REQUIRE(legacy || (s->view.n_tri == 0 && !s->view.legacy_spheres), "v2 shading models need a v2 sphere scene");
     PT_REQUIRE(!legacy || s->view.n_sph == 0 || s->view.legacy_spheres, "legacy shading needs legacy (textured) spheres");
@@ -455,6 +459,8 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
     const int mode = p->reserved[0] != PT_MODE_AUTO ? p->reserved[0] : PT_MODE_PERSIST;
     PT_REQUIRE(p->shading_model != PT_SHADE_V2_NORMALS || mode >= PT_MODE_PERSIST,
                "PT_SHADE_V2_NORMALS needs a persistent kernel (mode 0, 3, 4 or 5)");
+    const bool stage = p->shading_model == PT_SHADE_LEGACY_STAGE6 || p->shading_model == PT_SHADE_LEGACY_STAGE7;
+    PT_REQUIRE(!stage || mode == PT_MODE_PERSIST, "PT_SHADE_LEGACY_STAGE6/7 need the persistent kernel (mode 0 or 3)");
     PT_CUDA(cudaSetDevice(ctx->device));
 
     // reserved[4], [5]: a band of rows [row0, row1) instead of the whole frame (0, 0 = all rows) — the multi-GPU path
@@ -474,13 +480,14 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
     if (rc_pool) return rc_pool;
 
     RenderConsts rc;
-    rc.cam = make_camera(cam, p->width, p->height, (p->flags & PT_FLAG_PIXEL_GRID) != 0);
+    rc.cam = make_camera(cam, p->width, p->height, (p->flags & PT_FLAG_PIXEL_GRID) ? 1 : 0);
     rc.total_paths = total;
     rc.W = p->width; rc.H = p->height;
     rc.seed = p->seed; rc.spp_offset = (uint32_t)p->spp_offset;
     rc.max_depth = p->max_depth; rc.shading_model = p->shading_model;
     rc.absorptivity = p->absorptivity;
     rc.tmin = legacy ? nextafterf(PT_EPS, 1.0f) : PT_EPS;  // legacy accepts t > eps, v2 t >= 1e-4
+    if (stage) rc.tmin = nextafterf(1e-3f, 1.0f);          // legacy tutorial stages: record.t > 1e-3 (7_reflect.py:148)
     rc.pool_cap = (unsigned)cap;
     rc.accum_sq = want_sq ? 1 : 0;
     const unsigned long long WH = (unsigned long long)p->width * p->height;
@@ -673,12 +680,19 @@ extern "C" int pt_random_rays_device(PtContext* ctx, void* rays_dev, int64_t n, 
 
 extern "C" int pt_generate_rays(PtContext* ctx, const PtCamera* cam, int width, int height, int sample,
                                 uint32_t seed, float* rays_host) {
+    return pt_generate_rays_ex(ctx, cam, width, height, sample, seed, 0, rays_host);
+}
+
+extern "C" int pt_generate_rays_ex(PtContext* ctx, const PtCamera* cam, int width, int height, int sample,
+                                   uint32_t seed, int flags, float* rays_host) {
     PT_REQUIRE(ctx && cam && rays_host && width > 0 && height > 0, "bad argument");
+    PT_REQUIRE(!(flags & PT_FLAG_PIXEL_GRID) || (width >= 2 && height >= 2), "PT_FLAG_PIXEL_GRID needs width, height >= 2");
+    const int lattice = (flags & PT_FLAG_RAYS_FAST) ? 2 : (flags & PT_FLAG_PIXEL_GRID) ? 1 : 0;
     PT_CUDA(cudaSetDevice(ctx->device));
     const size_t n = (size_t)width * height;
     float4* d = nullptr;
     PT_CUDA(cudaMalloc(&d, n * 2 * sizeof(float4)));
-    k_generate_rays<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(make_camera(cam, width, height), width, height,
+    k_generate_rays<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(make_camera(cam, width, height, lattice), width, height,
                                                                          (uint32_t)sample, seed, d);
     cudaError_t e = cudaMemcpyAsync(rays_host, d, n * 2 * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -241,7 +241,10 @@ class TextureManager:
             p = resolve_asset(file_path) or resolve_asset(file_path + "_albedo.png") or resolve_asset(file_path + "_metallic.png")
             if p is None:
                 raise FileNotFoundError(file_path)
-            size = _open_image(p).size  # (width, height), as img.shape[1], img.shape[0]
+            if p.lower().endswith(".exr"):  # PIL has no EXR reader; the reference goes through imageio (15_module.py:463-467)
+                size = load_environment_image(p).shape[:2]
+            else:
+                size = _open_image(p).size  # (width, height), as img.shape[1], img.shape[0]
         self.configs.append({"file_path": file_path, "size": (int(size[0]), int(size[1])), "id": int(id)})
 
     def clear(self):
@@ -361,6 +364,13 @@ class Camera:
         from .render import default_context
         ctx = ctx or default_context()
         return ctx.generate_rays(self.to_struct(), self.resolution[0], self.resolution[1], int(sample), int(seed))
+
+    def get_rays_fast(self, ctx=None):
+        """Camera.get_rays_fast (15_module.py:423-436): one un-jittered pinhole ray per pixel through (i/W, j/H) of the
+        view rectangle at focal length 1 (the lens settings are ignored); float32 [H*W, 8] = o, tmin, d, tmax."""
+        from .render import default_context
+        ctx = ctx or default_context()
+        return ctx.generate_rays(self.to_struct(), self.resolution[0], self.resolution[1], 0, 0, _lib.PT_FLAG_RAYS_FAST)
 
 
 def reference_visit_order(tree, n_faces) -> np.ndarray:

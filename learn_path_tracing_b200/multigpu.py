@@ -32,6 +32,19 @@ def _dist_active(group=None) -> bool:
     return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
 
 
+def _reduce(t, dst, group):
+    """dist.reduce(SUM) of a contiguous tensor.  NCCL reduces device memory in place over NVLink; a process group that
+    cannot (gloo with CUDA tensors: the 1-GPU form of the multi-rank test) is served through a host copy."""
+    import torch.distributed as dist
+    if t.is_cuda and dist.get_backend(group) != "nccl":
+        h = t.cpu()
+        dist.reduce(h, dst=dst, op=dist.ReduceOp.SUM, group=group)
+        if dist.get_rank(group) == dst:
+            t.copy_(h)
+        return
+    dist.reduce(t, dst=dst, op=dist.ReduceOp.SUM, group=group)
+
+
 def reduce_accumulators(accum, dst: int = 0, group=None, channels: int = 4):
     """Sum the per-rank accumulators ([H*W,4] float: r, g, b, contributing paths) onto `dst`, in place.  channels=3
     ships only the radiance (the path count is a diagnostic): 25 % fewer bytes over NVLink at the price of one
@@ -40,10 +53,10 @@ def reduce_accumulators(accum, dst: int = 0, group=None, channels: int = 4):
     if not _dist_active(group):
         return accum
     if channels >= accum.shape[-1]:
-        dist.reduce(accum, dst=dst, op=dist.ReduceOp.SUM, group=group)
+        _reduce(accum, dst, group)
         return accum
     rgb = accum[:, :channels].contiguous()
-    dist.reduce(rgb, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    _reduce(rgb, dst, group)
     if dist.get_rank(group) == dst:
         accum[:, :channels].copy_(rgb)
     return accum
@@ -88,7 +101,7 @@ def render_split_reduce(renderer, scene, cam_struct, spp: int, max_depth: int, m
         ev.record(main)
         with torch.cuda.stream(side):  # band b travels while band b + 1 renders
             side.wait_event(ev)
-            dist.reduce(rows[y0:y1], dst=0, op=dist.ReduceOp.SUM, group=group)  # whole rows are contiguous: no packing
+            _reduce(rows[y0:y1], 0, group)  # whole rows are contiguous: no packing
     main.wait_stream(side)
     return offset, count
 

@@ -112,14 +112,14 @@ class Renderer:
 
 def render(world, camera, spp: int = 8192, propagate_limit: int = 32, seed: int = 1, bsdf=None,
            ctx: _lib.Context | None = None, return_stats: bool = False, postprocess: bool = True,
-           pixel_grid: bool = False):
+           pixel_grid: bool = False, absorptivity: float = 0.25, aces: bool = True):
     """Drop-in for the v2 scripts' render(world, camera) + post_processing(): returns the tonemapped
     image as a float32 [W,H,3] array in Taichi field layout (pass it to imwrite)."""
     ctx = ctx or default_context()
     w, h = camera.resolution
     model = getattr(bsdf, "shading_model", _lib.PT_SHADE_V2)
     r = Renderer(w, h, ctx)
-    st = r.render(world.device_scene(ctx), camera.to_struct(), spp, propagate_limit, model, seed,
+    st = r.render(world.device_scene(ctx), camera.to_struct(), spp, propagate_limit, model, seed, absorptivity=absorptivity,
                   flags=_lib.PT_FLAG_PIXEL_GRID if pixel_grid else 0)  # stages 2-4: lattice rays, no jitter
-    img = r.image(aces=True, gamma=2.2) if postprocess else r.mean()  # stages <= 5 write the linear image
+    img = r.image(aces=aces, gamma=2.2) if postprocess else r.mean()  # stages <= 5 write the linear image
     return (img, st) if return_stats else img

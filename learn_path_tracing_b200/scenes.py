@@ -25,9 +25,8 @@ def _six_spheres(with_glass=True, ground_y=-10000.5):
 
 
 def scene_2_camera_and_ray(resolution=(1280, 720)):
-    """2_camera_and_ray/__main__.py:26-28 — no world at all, the camera pitched up by 30 degrees looks at the sky.
-    (A scene cannot be empty here; the one sphere sits behind the camera where no ray can meet it.)"""
-    w = World([Sphere(Vec3f([0.0, -10.0, 10.0]), 0.5)])
+    """2_camera_and_ray/__main__.py:26-28 — an empty World(): the camera pitched up by 30 degrees looks at the sky."""
+    w = World()
     cam = Camera(resolution)
     cam.set_direction(0, 30, 0)
     return w, cam
@@ -47,6 +46,34 @@ def scene_5_anti_aliasing(resolution=(1280, 720)):
     cam = Camera(resolution)
     cam.set_direction(0, 0)
     cam.set_position(Vec3f([0, 0, 3]))
+    return w, cam
+
+
+def scene_legacy_6_diffuse(resolution=(400, 225)):
+    """legacy/PT_in_one_weekend/6_diffuse.py:185-189 — two albedo-only spheres, legacy (half-angle) camera at the origin,
+    fov 60, looking down -z; rendered with LegacyStage6BSDF, absorptivity 0.5, depth 100, gamma only."""
+    from . import legacy
+    w = World([Sphere(Vec3f([0.0, 0.0, -1.0]), 0.5, Vec3f([0.5, 0.5, 1.0])), Sphere(Vec3f([0, -100.5, -1]), 100, Vec3f([1, 1, 1]))])
+    cam = legacy.Camera(resolution, fov=60)
+    cam.set_direction(0, 0)
+    return w, cam
+
+
+def scene_legacy_7_reflect(resolution=(400, 225)):
+    """legacy/PT_in_one_weekend/7_reflect.py:228-236 — three spheres on a metallic ground, legacy camera at (0, -0.5, 4)...
+    (the committed 7_reflect.png is a 400x225 render; fov 45 is the HALF angle: view width 2 tan 45 = 2);
+    rendered with LegacyStage7BSDF, absorptivity 0.5, depth 100, gamma only."""
+    from . import legacy
+
+    def mat(albedo, roughness, metallic):
+        return Material(albedo=Vec3f(albedo), roughness=roughness, metallic=metallic, ior=1.5)
+    w = World([Sphere(Vec3f([0.0, 0.0, 0.0]), 0.5, material=mat([0.5, 0.5, 1], 1, 0)),
+               Sphere(Vec3f([-1.0, 0.0, 0.0]), 0.5, material=mat([0.5, 1, 0.5], 0, 1)),
+               Sphere(Vec3f([1.0, 0.0, 0.0]), 0.5, material=mat([1, 0.5, 0.5], 0.25, 1)),
+               Sphere(Vec3f([0, -10000.5, 0.0]), 10000, material=mat([0.5, 0.5, 0.5], 0.2, 1))])
+    cam = legacy.Camera(resolution, fov=45)
+    cam.set_direction(0, 0)
+    cam.set_position(Vec3f([0, -0.5, 4]))
     return w, cam
 
 
@@ -127,4 +154,5 @@ def scene_10_final(resolution=(1280, 720), seed=20261018):
 # stages 2-4 shoot one ray per pixel through the lattice i/(W-1), j/(H-1) (render(..., pixel_grid=True), spp=1)
 SCENES = {"2_camera_and_ray": scene_2_camera_and_ray, "3_adding_a_sphere": scene_3_adding_a_sphere,
           "4_objects": scene_5_anti_aliasing, "5_anti_aliasing": scene_5_anti_aliasing, "6_diffuse": scene_6_diffuse, "7_reflect": scene_7_reflect, "8_refract": scene_8_refract,
-          "9_dof": scene_9_dof, "10_final": scene_10_final}
+          "9_dof": scene_9_dof, "10_final": scene_10_final,
+          "legacy_6_diffuse": scene_legacy_6_diffuse, "legacy_7_reflect": scene_legacy_7_reflect}

@@ -525,6 +525,54 @@ static inline void scatter_legacy(const LegacyHit* h, V3* ro, V3* rd, V3* l, con
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* legacy tutorial stages 6 / 7 — ref: legacy/PT_in_one_weekend/7_reflect.py:49-96,139-209,    */
+/* 6_diffuse.py:106-170.  Same cal_reflectivity_*, sample_in_sphere, sample_diffuse as          */
+/* 15_module.py:281-334; pinned on the reference's own 6_diffuse.png / 7_reflect.png            */
+/* ------------------------------------------------------------------------------------------ */
+/* World.hit (7_reflect.py:139-150): near root only (:160-176), accepted iff t > 1e-3, first wins ties */
+static inline int world_hit_stage(const float* cr, int n, V3 ro, V3 rd, float* t_out) {
+    int best = -1;
+    float bt = -1.0f;
+    for (int i = 0; i < n; ++i) {
+        float t = sphere_hit_t(ro, rd, vload(cr + 4 * i), cr[4 * i + 3], 0);
+        if (t > 1e-3f && (bt < 0.0f || t < bt)) { bt = t; best = i; }
+    }
+    *t_out = bt;
+    return best;
+}
+static inline V3 sample_reflect_stage7(V3 dir, V3 n, float roughness, V3 s) { /* 7_reflect.py:91-96 */
+    float k = -vdot(dir, n);
+    V3 nd = vadd(dir, vscale(n, 2.0f * k));
+    return vnormalized(vadd(nd, vscale(s, k * roughness)));
+}
+/* propagate_once hit branch: 7_reflect.py:187-204 (model STAGE7), 6_diffuse.py:164-167 (model STAGE6) */
+static inline void scatter_stage(const PtMaterial* m, int model, float absorptivity, V3 point, V3 n, V3* ro, V3* rd, V3* l,
+                                 const float u[4], const float u2[4]) {
+    V3 d = *rd, albedo = vload(m->albedo);
+    *ro = point;
+    if (model == PT_SHADE_LEGACY_STAGE6) {
+        *rd = vnormalized(vadd(n, sample_at_sphere(u[2], u[3])));
+        *l = vmul(vscale(*l, absorptivity), albedo);
+        return;
+    }
+    float w = pow5(1.0f + vdot(n, d));
+    if (m->metallic) {
+        V3 F = v3(albedo.x + (1.0f - albedo.x) * w, albedo.y + (1.0f - albedo.y) * w, albedo.z + (1.0f - albedo.z) * w);
+        *rd = sample_reflect_stage7(d, n, m->roughness, sample_in_sphere(u[2], u[3], u2[0]));
+        *l = vmul(*l, F);
+    } else {
+        float f0 = ((m->ior - 1.0f) / (m->ior + 1.0f)) * ((m->ior - 1.0f) / (m->ior + 1.0f));
+        float F = f0 + (1.0f - f0) * w;
+        if (u[1] > F) {
+            *rd = vnormalized(vadd(n, sample_at_sphere(u[2], u[3])));
+            *l = vmul(*l, vscale(albedo, absorptivity));
+        } else {
+            *rd = sample_reflect_stage7(d, n, m->roughness, sample_in_sphere(u[2], u[3], u2[0]));
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* render — ref: v2 __main__.py:65-87,99-103; legacy:980-1036                                  */
 /* ------------------------------------------------------------------------------------------ */
 static inline int finite3(V3 c) { return isfinite(c.x) && isfinite(c.y) && isfinite(c.z); }
@@ -574,6 +622,19 @@ int orc_render(const OrcScene* sc, const PtCamera* cam, const PtRenderParams* p,
                         } else { /* :990-991 */
                             V3 e = sc->env ? environment_color(sc, rd) : background_color(rd);
                             radiance = vmul(e, l);
+                            ended = 1;
+                            break;
+                        }
+                    } else if (p->shading_model == PT_SHADE_LEGACY_STAGE6 || p->shading_model == PT_SHADE_LEGACY_STAGE7) {
+                        float t;
+                        int id = world_hit_stage(sc->sph_cr, sc->n_sph, ro, rd, &t);
+                        tot_prims += (uint64_t)sc->n_sph;
+                        if (id >= 0) {
+                            V3 point = vadd(ro, vscale(rd, t));
+                            V3 normal = vnormalized(vsub(point, vload(sc->sph_cr + 4 * id)));
+                            scatter_stage(sc->sph_mat + id, p->shading_model, p->absorptivity, point, normal, &ro, &rd, &l, u, u2);
+                        } else {
+                            radiance = vmul(background_color(rd), l);
                             ended = 1;
                             break;
                         }

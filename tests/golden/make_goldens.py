@@ -34,7 +34,12 @@ def main(ref="/root/reference"):
         print(out, os.path.getsize(out), "bytes")
     # the legacy tutorial stages with the legacy camera (half-angle fov, 15_module.py:397-401 has the same formula):
     # 3 and 4 are deterministic lattice renders, 5 is 100 spp of normals as colours
-    for s in ["3_adding_a_sphere", "4_objects", "5_anti_aliasing"]:
+    # 6_diffuse.png is the converged (8192 spp) render of legacy 6_diffuse.py as committed: pins the legacy scattering
+    # helpers shared with 15_module.py (sample_at_sphere, sample_diffuse), the t > 1e-3 hit rule and the 0.5 * albedo
+    # throughput.  7_reflect.png was rendered with OTHER scene/camera settings than the committed 7_reflect.py (the horizon
+    # lies 24.5 rows below the centre; the script's radius-10000 ground under a level camera puts it at the centre): only
+    # its sky rows (camera with fov 45 = half angle, gamma 2.2, rounding cast) are usable as a pin.
+    for s in ["3_adding_a_sphere", "4_objects", "5_anti_aliasing", "6_diffuse", "7_reflect"]:
         im = Image.open(os.path.join(ref, "legacy", "PT_in_one_weekend", s + ".png")).convert("RGB")
         out = os.path.join(here, f"legacy_{s}_{im.size[0]}x{im.size[1]}.png")
         im.save(out, optimize=True)

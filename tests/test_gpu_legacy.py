@@ -80,7 +80,7 @@ def test_synthetic_scene_hits_match_reference_traversal(ctx, oracle):
     assert n_prims == 2 + 2 * 14 * 14 + 2 and n_global >= 2  # the +-50 ground triangles stay out of the LBVH
 
 
-@pytest.mark.parametrize("name", ["demo", "yoimiya_ground_small", "zhongli_small"])
+@pytest.mark.parametrize("name", ["demo", "yoimiya_ground_small", "zhongli_small", "ganyu_small"])
 def test_cached_scene_hits_match_reference_traversal(ctx, oracle, name):
     world = cached_world(name)
     if world is None:
@@ -128,7 +128,7 @@ def test_synthetic_scene_image_within_3_sigma(ctx, oracle, absorptivity):
     assert rmse < 6.0
 
 
-@pytest.mark.parametrize("name,spp", [("demo", 128), ("yoimiya_ground_small", 64), ("zhongli_small", 64)])
+@pytest.mark.parametrize("name,spp", [("demo", 128), ("yoimiya_ground_small", 64), ("zhongli_small", 64), ("ganyu_small", 64)])
 def test_cached_scene_image_within_3_sigma(ctx, oracle, name, spp):
     world = cached_world(name)
     if world is None:

@@ -196,3 +196,34 @@ def test_legacy_oracle_white_furnace(oracle):
     assert m.max() <= 0.5 + 1e-4 and m.mean() > 0.45
     tris, off = all_triangles(w)
     assert off == 2 and tris.shape[1] == 9
+
+
+def test_exr_environment_round_trip(tmp_path):
+    """SURVEY 8f-2 / 15_module.py:118-132,1049: an EXR environment (float radiance, not /255) goes through
+    TextureManager.add -> build -> load_environment exactly like the reference's imageio path: indexed [x, y] with y up,
+    RGB order, values untouched.  The two EXRs the reference scripts name are missing from the checkout, so a small one
+    is written here with cv2 (the reader legacy.py uses)."""
+    import os
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    rgb = (rng.random((32, 64, 3)) * 6.0).astype(np.float32)      # rows x columns x RGB, values above 1 (HDR)
+    fn = str(tmp_path / "env_small.exr")
+    assert cv2.imwrite(fn, rgb[:, :, ::-1])                         # cv2 stores BGR
+    img = legacy.load_environment_image(fn)
+    assert img.shape == (64, 32, 3) and img.dtype == np.float32
+    # reference: env.transpose(1, 0, 2) then flip along y -> img[x, y] = rgb[H-1-y, x]
+    assert np.array_equal(img, np.flip(rgb.transpose(1, 0, 2), 1))
+    w = legacy.World(environment_size=(128, 64))
+    w.environments.add(fn, 0)                                       # size read from the EXR itself
+    w.set_environment(0)
+    w.environments.build()
+    w.load_textures()
+    env, area = w._env
+    assert area == [0, 0, 64, 32] and env.shape == (128, 64, 3)
+    assert np.array_equal(env[:64, :32], img) and float(np.abs(env[64:]).max()) == 0.0
+    # the oracle's bilinear lookup returns the texel value at texel centres (weights 1,0,0,0): u = (x + .5) / w
+    from oracle import ptoracle as O
+    if hasattr(O, "environment_lookup"):
+        d = np.array([[0.0, 0.0, -1.0]], np.float32)
+        assert np.isfinite(O.environment_lookup(env, area, d)).all()

@@ -149,3 +149,56 @@ def test_rng_is_counter_based_and_uniform(oracle):
     assert not np.array_equal(a, oracle.rng4(5, 7, 2, 99))
     u = np.stack([oracle.rng4(i, 0, 0, 1) for i in range(4096)])
     assert abs(u.mean() - 0.5) < 0.01 and abs(u.var() - 1 / 12) < 0.005
+
+
+def test_legacy_6_diffuse_png_pins_the_legacy_scattering_helpers(oracle):
+    """legacy/PT_in_one_weekend/6_diffuse.png is the reference's converged render (400x225, 8192 spp, depth 100) of the
+    script as committed (6_diffuse.py:12-14,160-170,185-189).  It uses the functions 15_module.py still carries —
+    sample_at_sphere / sample_diffuse (:295-325), the half-angle legacy camera — plus the tutorial's hit rule (t > 1e-3,
+    near root) and throughput 0.5 * albedo.  The oracle's PT_SHADE_LEGACY_STAGE6 at 256 spp, gamma 2.2, ROUNDING cast (the
+    legacy ti.imwrite) lands on it: measured rmse 1.20 / 255 (Monte Carlo noise of 256 spp), bias -0.01, 8x8-box rmse
+    0.15; with gamma 2.0 the bias is -5, with ACES + gamma -31, flipped > 30: a real pin of the model, not of the noise."""
+    W, H, SPP = 400, 225, 256
+    world, cam = scenes.scene_legacy_6_diffuse((W, H))
+    acc, _, st = oracle.render(oracle.scene_from_world(world), cam.to_struct(), W, H, SPP, 100, L.PT_SHADE_LEGACY_STAGE6, seed=1,
+                               absorptivity=0.5)
+    gold = np.asarray(Image.open(os.path.join(GOLDEN, f"legacy_6_diffuse_{W}x{H}.png")).convert("RGB"), np.float64)
+    img = L.to_uint8(np.power(acc / SPP, np.float32(1 / 2.2)), rounding=True).astype(np.float64)
+    d = img - gold
+    box = d[:224, :400].reshape(28, 8, 50, 8, 3).mean(axis=(1, 3))
+    assert np.sqrt((d**2).mean()) < 1.6 and abs(d.mean()) < 0.08 and np.sqrt((box**2).mean()) < 0.3, \
+        (np.sqrt((d**2).mean()), d.mean(), np.sqrt((box**2).mean()))
+    assert np.sqrt(((img[::-1] - gold) ** 2).mean()) > 30
+    wrong = L.to_uint8(np.sqrt(acc / SPP), rounding=True).astype(np.float64) - gold      # gamma 2.0 instead of 2.2
+    assert abs(wrong.mean()) > 3
+    assert 1.7 < st.segments / st.paths < 1.9
+
+
+def test_legacy_7_reflect_png_sky_rows_pin_the_camera_and_gamma(oracle):
+    """legacy/PT_in_one_weekend/7_reflect.png was NOT rendered from 7_reflect.py as committed (its horizon lies 24.5 rows
+    below the image centre; the script's level camera over a radius-10000 ground puts it at the centre; the ground is
+    diffuse there, metallic in the script), so its spheres cannot pin sample_reflect / cal_reflectivity_*.  Its sky rows
+    still pin the legacy camera at fov 45 (HALF angle: view width 2 tan 45 = 2), the sky gradient, gamma 2.2 and the
+    rounding cast: the top 40 rows are reproduced to <= 1 level."""
+    W, H, SPP = 400, 225, 16
+    world, cam = scenes.scene_legacy_7_reflect((W, H))
+    acc, _, _ = oracle.render(oracle.scene_from_world(world), cam.to_struct(), W, H, SPP, 100, L.PT_SHADE_LEGACY_STAGE7, seed=1,
+                              absorptivity=0.5)
+    gold = np.asarray(Image.open(os.path.join(GOLDEN, f"legacy_7_reflect_{W}x{H}.png")).convert("RGB"), np.float64)
+    img = L.to_uint8(np.power(acc / SPP, np.float32(1 / 2.2)), rounding=True).astype(np.float64)
+    d = (img - gold)[:40]
+    assert np.abs(d).max() <= 1 and (d == 0).mean() > 0.8, (np.abs(d).max(), (d == 0).mean())
+
+
+def test_legacy_stage7_scattering_statistics(oracle):
+    """PT_SHADE_LEGACY_STAGE7 (7_reflect.py:187-209) on the script's own scene: energy bookkeeping that follows from the
+    source alone — a metallic hit multiplies by F >= albedo, a diffuse hit by albedo * absorptivity, nothing is added, so the
+    image is bounded by the sky and darker with more absorption; the perfect mirror (roughness 0) sphere shows no noise at
+    its centre beyond the sky's own variation."""
+    W, H = 200, 112
+    world, cam = scenes.scene_legacy_7_reflect((W, H))
+    sc = oracle.scene_from_world(world)
+    a, _, sa = oracle.render(sc, cam.to_struct(), W, H, 32, 100, L.PT_SHADE_LEGACY_STAGE7, seed=1, absorptivity=0.5)
+    b, _, sb = oracle.render(sc, cam.to_struct(), W, H, 32, 100, L.PT_SHADE_LEGACY_STAGE7, seed=1, absorptivity=0.25)
+    assert a.max() / 32 <= 1.0 + 1e-5 and a.min() >= 0
+    assert b.mean() < a.mean() and sa.segments == sb.segments      # same paths, less throughput
