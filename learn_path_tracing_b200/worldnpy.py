@@ -23,13 +23,26 @@ class _Stub:
         self.__dict__.update(state if isinstance(state, dict) else {"_state": state})
 
 
+# what a .world.npy may name besides taichi.* (stubbed): numpy's array/dtype/scalar reconstructors and plain containers.
+# Anything else is refused — np.load(allow_pickle=True), which the reference uses, would execute it.
+_ALLOWED = {
+    ("numpy._core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "scalar"), ("numpy", "ndarray"), ("numpy", "dtype"),
+    ("numpy._core.numeric", "_frombuffer"), ("builtins", "dict"), ("builtins", "list"), ("builtins", "tuple"),
+    ("builtins", "set"), ("builtins", "frozenset"), ("builtins", "int"), ("builtins", "float"), ("builtins", "str"),
+    ("builtins", "bytes"), ("builtins", "bool"), ("builtins", "complex"), ("builtins", "slice"), ("collections", "OrderedDict"),
+}
+
+
 class _Unpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if module.startswith("taichi"):
             return type(name, (_Stub,), {"__module__": module})
         if module.startswith("numpy.core"):
             module = module.replace("numpy.core", "numpy._core")
-        return super().find_class(module, name)
+        if (module, name) in _ALLOWED or (module == "numpy" and name in np.sctypeDict):
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(f".world.npy names {module}.{name}: only numpy arrays, plain containers and taichi "
+                                     "structs are loaded")
 
 
 def _plain(x):
@@ -134,10 +147,10 @@ def save_world(filename, meshes: list[dict], environment: int, textures: dict | 
             "positions_field": field(m["positions"]), "normals_field": field(m["normals"]),
             "texture_coords_field": field(m["texcoords"]),
         })
-    if textures is not None:
-        out["textures"] = textures
-    if environments is not None:
-        out["environments"] = environments
+    # World.load (15_module.py:823-836) indexes data['textures'] / data['environments'] unconditionally: always present,
+    # as empty TextureManager.dump()-shaped dicts when the world has none
+    out["textures"] = textures if textures is not None else {"size": (0, 0), "configs": []}
+    out["environments"] = environments if environments is not None else {"size": (0, 0), "configs": []}
     if spheres is not None:
         out["spheres_bvh"] = spheres
     np.save(filename, out, allow_pickle=True)

@@ -234,6 +234,22 @@ def test_config4_10m_triangles_64m_rays(ctx, oracle):
         tg, wg = oracle.triangle_eval(tris, gid[bad].astype(np.int32), r_h[bad])
         to, wo = oracle.triangle_eval(tris, oid[bad].astype(np.int32), r_h[bad])
         tie = (gid[bad] >= 0) & (oid[bad] >= 0) & (np.abs(gt[bad] - ot[bad]) <= 1e-5 * np.abs(ot[bad]))
-        # barycentrics of a 0.004-sized triangle at coordinates ~1.5 carry ~16 ulp * 1.5 / 0.004 = 7e-4 of rounding
-        edge = ((gid[bad] >= 0) & (np.abs(wg) < 2e-3)) | ((oid[bad] >= 0) & (np.abs(wo) < 2e-3))
-        assert np.all(tie | edge), (int((~(tie | edge)).sum()), wg, wo)
+
+        def grazing(ids):
+            """|d.N| of the ray against the plane of triangle `ids` (1 where there is no triangle)."""
+            T = tris[np.maximum(ids, 0)]
+            n = np.cross(T[:, 3:6] - T[:, 0:3], T[:, 6:9] - T[:, 0:3])
+            n /= np.linalg.norm(n, axis=1, keepdims=True)
+            return np.where(ids >= 0, np.abs((r_h[bad][:, 4:7] * n).sum(1)), 1.0)
+        # barycentrics of a 0.004-sized triangle at coordinates ~1.5 carry ~16 ulp * 1.5 / 0.004 = 7e-4 of rounding, times
+        # 1 / |d.N| when the ray grazes the triangle's plane (the hit point moves along the ray by ulp(t) / |d.N|): the
+        # 2^22-ray sample contains rays within 0.3 degrees of a plane, the 2^16-ray sample of round 1 did not
+        dn_g, dn_o = grazing(gid[bad].astype(np.int64)), grazing(oid[bad].astype(np.int64))
+        edge = ((gid[bad] >= 0) & (np.abs(wg) < 2e-3 + 1e-3 / np.maximum(dn_g, 1e-9))) | \
+               ((oid[bad] >= 0) & (np.abs(wo) < 2e-3 + 1e-3 / np.maximum(dn_o, 1e-9)))
+        rest = ~(tie | edge)
+        assert not rest.any(), (int(rest.sum()), gid[bad][rest], oid[bad][rest], gt[bad][rest], ot[bad][rest], wg[rest], wo[rest],
+                                dn_g[rest], dn_o[rest])
+        assert len(bad) < 1e-4 * n_c
+        print(f"config4: {len(bad)} of {n_c} sampled rays differ from the oracle: {int(tie.sum())} ties, {int((edge & ~tie).sum())} edge / plane grazes "
+              f"(smallest |d.N| {min(dn_g.min(), dn_o.min()):.2e})")

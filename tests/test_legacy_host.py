@@ -227,3 +227,23 @@ def test_exr_environment_round_trip(tmp_path):
     if hasattr(O, "environment_lookup"):
         d = np.array([[0.0, 0.0, -1.0]], np.float32)
         assert np.isfinite(O.environment_lookup(env, area, d)).all()
+
+
+def test_world_npy_loader_refuses_foreign_classes_and_writes_both_manager_keys(tmp_path):
+    """the custom unpickler resolves only numpy arrays / plain containers / (stubbed) taichi structs — the
+    reference's np.load(allow_pickle=True) would execute anything; and World.save always writes 'textures' and
+    'environments' (the reference's World.load, 15_module.py:823-836, indexes both unconditionally)."""
+    import pickle
+
+    class Evil:
+        def __reduce__(self):
+            return (os.system, ("true",))
+    fn = str(tmp_path / "evil.world.npy")
+    np.save(fn, {"meshes_bvhs": [], "environment": 0, "x": Evil()}, allow_pickle=True)
+    with pytest.raises(pickle.UnpicklingError):
+        worldnpy.load_world(fn)
+    ok = str(tmp_path / "plain.world.npy")
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    worldnpy.save_world(ok, [{"positions": pos, "normals": pos, "texcoords": pos[:, :2], "faces": np.zeros((1, 10), np.int32)}], 0)
+    d = worldnpy.load_world(ok)
+    assert d["textures"]["configs"] == [] and d["environments"]["configs"] == [] and len(d["meshes_bvhs"]) == 1
