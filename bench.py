@@ -383,7 +383,7 @@ def measure_render(D, name, steps, warmup, args, cpu_seconds=0.0):
         "mrays_per_s": seg_total * steps / (t_max * 1e-3) / 1e6,
         "segments_per_path": seg_total / paths_total,
         "config": workload_config(name),
-        "parallelism": f"samples split x{ws} (strong), scene replicated" + (f", NCCL reduce in {bands} row band(s) overlapped with rendering" if ws > 1 else ""),
+        "parallelism": f"samples split x{ws} (strong), scene replicated" + ((f", one NCCL reduce (rgb) behind the render on the same stream" if bands == 1 else f", NCCL reduce in {bands} row bands overlapped with rendering") if ws > 1 else ""),
         "mode": int(stt.reserved[0]),
         "e2e": e2e, "gpu_launches": steps * bands, "clocks": clocks,
         "roofline": roof, "roofline_issue": issue_entry(nc),
@@ -562,7 +562,9 @@ def main():
     ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS) + sorted(INTERSECT))
     ap.add_argument("--only", action="store_true", help="measure --workload alone (no `workloads` entries)")
     ap.add_argument("--mode", type=int, default=0, help="render mode: 0 auto (= 3 persistent), 1 split kernels, 2 K-step fused, 3 persistent")
-    ap.add_argument("--bands", type=int, default=4, help="N > 1: row bands per frame; the reduce of a band overlaps the rendering of the next (1 = one reduce)")
+    ap.add_argument("--bands", type=int, default=1, help="N > 1: row bands per frame, the reduce of a band overlapping the rendering of the next "
+                    "(measured on 2 B200s: 1 band 34.9 / 4 bands 33.6 / 8 bands 31.5 Gpaths/s on 8_refract, 9.6 / 8.2 / 7.3 on Yoimiya: every band "
+                    "pays the ramp-up and tail of its own persistent launch, the reduce it hides is ~0.1 ms; hence 1)")
     ap.add_argument("--shade-min", type=int, default=0, help="persistent mode: waiting lanes that trigger shading (0 = default)")
     ap.add_argument("--serve-min", type=int, default=0, help="persistent mode: waiting lanes that trigger a service (0 = default)")
     ap.add_argument("--trace-flags", type=int, default=0, help="intersect workloads: PT_FLAG_* for pt_trace_batch_device")
