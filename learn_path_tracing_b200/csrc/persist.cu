@@ -259,6 +259,7 @@ k_trace_persist(const SceneView sv, const float4* __restrict__ rays, const unsig
                     if (QNODES) node_step_q<COUNT>(sv, T, stack, tc);
                     else node_step<COUNT>(sv, T, stack, tc);
                 }
+
             }
             continue;
         }
