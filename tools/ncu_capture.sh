@@ -20,7 +20,7 @@ for pair in "10_final_720p_8192:10_final_720p_8192" "8_refract_1080p:8_refract_1
   tail -2 $out/ncu_$name.log
 done
 if [ -z "$NCU_ONLY" ]; then
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/r02_launches_default_bench.csv \
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $out/r02_launches_default_bench.csv \
       python bench.py --steps 1 --no-cpu > $out/ncu_launches.log 2>&1
 fi
 ls -la $out
