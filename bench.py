@@ -49,6 +49,7 @@ WORKLOADS = {
 # BASELINE configs[4]: synthetic 10M-triangle scene, 64Mi-ray intersection-only batch
 INTERSECT = {"intersect_10m": (10_000_000, 64 * 2**20, 12345, 54321, 0.004),
              "intersect_1m": (1_000_000, 8 * 2**20, 12345, 54321, 0.0086)}
+SPP_OVERRIDE = 0   # --spp: A/B runs at another sample count (e.g. the per-GPU share of a split frame); never a bench line
 HEADLINE = "10_final_720p_8192"
 OTHERS = ["8_refract_1080p", "yoimiya_1080p", "zhongli_4k_4096", "intersect_10m"]
 KERNEL_OF = {"10_final_720p_8192": "k_paths_persist<V2>", "10_final_720p": "k_paths_persist<V2>", "8_refract_1080p": "k_paths_persist<V2>",
@@ -144,6 +145,7 @@ def workload_config(name):
         n_tri, n_rays, seed_t, seed_r, edge = INTERSECT[name]
         return {"workload": name, "triangles": n_tri, "rays": n_rays, "edge_scale": edge, "seeds": [seed_t, seed_r]}
     scene, W, H, spp, depth = WORKLOADS[name]
+    spp = SPP_OVERRIDE or spp
     return {"workload": name, "scene": scene, "width": W, "height": H, "spp": spp, "max_depth": depth,
             "l2": "GPU arm: 252 MB fill between timed steps; CPU arm: not applicable"}
 
@@ -153,6 +155,7 @@ def build_workload(name):
     import learn_path_tracing_b200 as L
     from learn_path_tracing_b200 import scenes
     scene, W, H, spp, depth = WORKLOADS[name]
+    spp = SPP_OVERRIDE or spp
     if scene.startswith("cache:"):
         from learn_path_tracing_b200 import legacy, scene_cache
         path = os.path.join(ROOT, "scenes_cache", scene[6:] + ".npz")
@@ -569,7 +572,10 @@ def main():
     ap.add_argument("--serve-min", type=int, default=0, help="persistent mode: waiting lanes that trigger a service (0 = default)")
     ap.add_argument("--trace-flags", type=int, default=0, help="intersect workloads: PT_FLAG_* for pt_trace_batch_device")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
+    ap.add_argument("--spp", type=int, default=0, help="A/B runs only: override the workload's samples per pixel (config.spp shows it)")
     args = ap.parse_args()
+    global SPP_OVERRIDE
+    SPP_OVERRIDE = max(0, args.spp)
     if args.impl == "reference":
         run_reference(args)
     else:

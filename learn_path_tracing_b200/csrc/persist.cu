@@ -17,8 +17,8 @@
 //                    and generate their camera ray in place (fused ray generation)
 //     refill         (trace kernel) finished lanes write their hit record and draw the next ray
 //
-// A work unit of the render kernel is one 8x4 pixel tile x 16 samples, taken from ONE global counter
-// (one atomic per 512 paths); the lanes of a warp therefore always look at the same 32 pixels, which
+// A work unit of the render kernel is one 8x4 pixel tile x 4-16 samples (fewer in short launches), taken from ONE global counter
+// (one atomic per 128-512 paths); the lanes of a warp therefore always look at the same 32 pixels, which
 // keeps their rays — and their behaviour (all sky, all ground, all mesh) — alike.  One launch renders
 // everything: no path pool in HBM, no per-bounce launches; HBM only sees the scene and the accumulator.
 // The RNG is keyed on (pixel, sample, bounce), so the image is the same set of paths as the other modes.
@@ -35,9 +35,7 @@
 
 #define PT_TILE_W 8
 #define PT_TILE_H 4
-#ifndef PT_UNIT_SAMPLES
-#define PT_UNIT_SAMPLES 16
-#endif
+// samples per work unit: RenderConsts::unit_samples (chosen per launch in wavefront.cu:pt_render)
 
 // WIDE (experimental, `make EXPERIMENTAL=1` + PT_WIDE=1 when the scene is built + PT_FLAG_WIDE): the node phase walks the
 // 4-wide copy of the tree (extend.cuh:node_step4).  Measured on the B200 in round 2 (profiles/r02_ab_wide.txt): same
@@ -83,7 +81,7 @@ k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* _
     const unsigned lt = (1u << lane) - 1u;
     const unsigned tiles_x = ((unsigned)rc.W + PT_TILE_W - 1) / PT_TILE_W, tiles_y = ((unsigned)(rc.row1 - rc.row0) + PT_TILE_H - 1) / PT_TILE_H;
     const unsigned spp = rc.sample_end - rc.spp_offset;
-    const unsigned n_chunks = (spp + PT_UNIT_SAMPLES - 1) / PT_UNIT_SAMPLES;
+    const unsigned n_chunks = (spp + rc.unit_samples - 1) / rc.unit_samples;
     const unsigned long long n_units = (unsigned long long)tiles_x * tiles_y * n_chunks;
     PathState p;
     Trav T;
@@ -167,8 +165,8 @@ k_paths_persist(const SceneView sv, const RenderConsts rc, unsigned long long* _
                     const unsigned ty = tile / tiles_x;
                     unit_x0 = (tile - ty * tiles_x) * PT_TILE_W;
                     unit_y0 = (unsigned)rc.row0 + ty * PT_TILE_H;
-                    unit_s0 = chunk * PT_UNIT_SAMPLES;
-                    unit_ns = min((unsigned)PT_UNIT_SAMPLES, spp - unit_s0);
+                    unit_s0 = chunk * rc.unit_samples;
+                    unit_ns = min(rc.unit_samples, spp - unit_s0);
                     unit_size = unit_ns * 32u;
                     unit_next = 0u;
                 }

@@ -20,6 +20,7 @@
 // survivors of a launch go through the ballot/prefix-sum compaction into the HBM pool.  Sample ids are
 // strided statically (path id, id + P, id + 2P, ... per pool slot), so regeneration needs no atomics.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "wf_common.cuh"
@@ -495,6 +496,17 @@ extern "C" int pt_render(PtContext* ctx, const PtScene* s, const PtCamera* cam, 
     rc.stride_pixels = (uint32_t)(cap % WH);
     rc.sample_end = (uint32_t)(p->spp_offset + p->spp);
     rc.row0 = row0; rc.row1 = row1;
+    {   // Work unit of the persistent kernel = one 8x4 tile x unit_samples.  A launch ends when its LAST unit ends, and a
+        // unit over the heaviest tile runs several times the average, so a short launch (the per-GPU share of a
+        // sample-split frame: 8_refract 32 spp, Yoimiya 64 spp on 8 GPUs) spends a visible part of its time in that
+        // tail: fewer samples per unit there.  Same-box sweep (profiles/r02_ab_unit_samples.txt): Yoimiya at 64 spp 4204
+        // (16) / 4633 (8) / 4688 (4) Mpaths/s, Zhongli 4K at 64 spp 7567 / 8018 / 8130, 8_refract at 32 spp 16482 / 16749 /
+        // 16542; from 256 spp on 16 is best everywhere (fewest counter atomics).  PT_UNIT_SAMPLES overrides (A/B runs).
+        const char* ue = getenv("PT_UNIT_SAMPLES");
+        int us = ue ? atoi(ue) : 0;
+        if (us < 1 || us > 64) us = p->spp >= 256 ? 16 : (!legacy || p->spp >= 128 ? 8 : 4);
+        rc.unit_samples = (uint32_t)us;
+    }
 
     cudaStream_t st = ctx->stream;
     const bool timing = (p->flags & PT_FLAG_TIMING) != 0;

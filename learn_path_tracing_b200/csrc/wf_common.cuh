@@ -36,6 +36,7 @@ struct RenderConsts {
     uint32_t stride_samples, stride_pixels;  // pool_cap = stride_samples * W*H + stride_pixels
     uint32_t sample_end;                     // spp_offset + spp
     int row0, row1;                          // rows [row0, row1) of the image are rendered (persistent kernel; else 0, H)
+    uint32_t unit_samples;                   // persistent kernel: samples per work unit (one 8x4 tile x unit_samples)
 };
 
 struct PoolPtrs {
