@@ -85,20 +85,20 @@ class ImageField:
         self.host = None
 
     # -- booking
-    def book(self, world, rays, spp, depth, model):
+    def book(self, world, rays, spp, depth, model, flags=0):
         if rays.camera is None:
             raise RuntimeError("shader(world, rays) before camera.get_rays(rays)")
         self.norm = int(spp)
         self.host = None
         last = self.booked[-1] if self.booked else None
-        if last and last[0] is world and last[2] == rays.camera_key and last[4] == depth and last[5] == model:
+        if last and last[0] is world and last[2] == rays.camera_key and last[4] == depth and last[5] == model and last[7] == flags:
             last[6] += 1
         else:
-            self.booked.append([world, rays.camera, rays.camera_key, int(spp), int(depth), int(model), 1])
+            self.booked.append([world, rays.camera, rays.camera_key, int(spp), int(depth), int(model), 1, int(flags)])
 
     def flush(self):
-        for world, cam, _, _, depth, model, count in self.booked:
-            self.renderer = _render_pass(self, world, cam, count, depth, model, self.done)
+        for world, cam, _, _, depth, model, count, flags in self.booked:
+            self.renderer = _render_pass(self, world, cam, count, depth, model, self.done, flags)
             self.done += count
         self.booked = []
 
@@ -124,12 +124,12 @@ class ImageField:
             self.renderer.clear()
 
 
-def _render_pass(image, world, cam, count, depth, model, first_sample):
+def _render_pass(image, world, cam, count, depth, model, first_sample, flags=0):
     """`count` more samples per pixel of (world, cam) into the image's device accumulator: ONE pt_render call."""
     w, h = image.shape
     r = image.renderer or L.Renderer(w, h, L.default_context())
     r.render(world.device_scene(r.ctx), cam, count, depth, model, seed=int(os.environ.get("LPT_SEED", "1")),
-             spp_offset=first_sample, want_stats=False)
+             spp_offset=first_sample, want_stats=False, flags=flags)
     return r
 
 
@@ -145,6 +145,7 @@ def _read_image(image):
 class Kernel:
     """@ti.kernel: classified by what its body refers to.
        shading pass   body reaches world.hit / a BSDF's sample (through the script's @ti.func bodies): books one sample
+                      (stages 6-10: the BSDFs named decide the model; stages 4-5 name none: normals as colours)
        post pass      body calls ACES_tonemapping / gamma_correction: marks the image as post-processed"""
 
     def __init__(self, fn):
@@ -159,6 +160,8 @@ class Kernel:
     def model(self):
         if "DiffuseBSDF" in self.names and "MetalBSDF" not in self.names:
             return L.PT_SHADE_V2_DIFFUSE
+        if not {"MetalBSDF", "DielectricBSDF", "DiffuseBSDF"} & self.names:
+            return L.PT_SHADE_V2_NORMALS      # stages 4-5: ray_color() shows hit.normal, nothing scatters
         return L.PT_SHADE_V2
 
     def __call__(self, *args):
@@ -167,9 +170,14 @@ class Kernel:
         if not isinstance(image, ImageField):
             raise RuntimeError(f"kernel {self.__name__}: no image field among the script's globals")
         if self.kind == "shade":
-            world = next(a for a in args if isinstance(a, L.World))
+            world = next((a for a in args if isinstance(a, L.World)), None)
+            if world is None:
+                raise NotImplementedError(f"kernel {self.__name__}: no World among its arguments (stages 2-3 intersect a sphere "
+                                          "typed into their own device code: use compat/taichi_pathtracer/{2,3}_* instead)")
             rays = next(a for a in args if isinstance(a, RayField))
-            image.book(world, rays, g["spp"], g["propagate_limit"], self.model())
+            # stage 4 has no `spp`: ONE un-jittered ray per pixel through the lattice i/(W-1) (4_objects/camera.py), image = colour
+            flags = 0 if "spp" in g else L.PT_FLAG_PIXEL_GRID
+            image.book(world, rays, g.get("spp", 1), g.get("propagate_limit", 1), self.model(), flags)
         elif self.kind == "post":
             image.flush()
             image.post = ("ACES_tonemapping" in self.names, 2.2 if "gamma_correction" in self.names else 1.0)

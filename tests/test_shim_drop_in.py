@@ -37,8 +37,8 @@ def _run(stage, tmp_path, monkeypatch, fake=True):
     import _runtime
     calls = []
     if fake:
-        def render_pass(image, world, cam, count, depth, model, first_sample):
-            calls.append(("render", world, cam, count, depth, model, first_sample, image.shape))
+        def render_pass(image, world, cam, count, depth, model, first_sample, flags=0):
+            calls.append(("render", world, cam, count, depth, model, first_sample, image.shape, flags))
             return None
 
         def read_image(image):
@@ -58,7 +58,7 @@ def test_unmodified_10_final_script_collapses_into_one_render_pass(tmp_path, mon
     g, calls = _run("10_final", tmp_path, monkeypatch)
     renders = [c for c in calls if c[0] == "render"]
     assert len(renders) == 1
-    _, world, cam, count, depth, model, first, shape = renders[0]
+    _, world, cam, count, depth, model, first, shape, _flags = renders[0]
     assert (count, depth, model, first, shape) == (8192, 32, L.PT_SHADE_V2, 0, (1280, 720))   # the script's own globals
     assert 470 <= world.size <= 490 and world.spheres[0].radius == 10000                        # random_scene(): ground first
     assert [round(float(x), 4) for x in cam.pos] == [13.0, 2.0, 3.0] and abs(cam.focal_length - 10.0) < 1e-6 and abs(cam.aperture - 0.2) < 1e-6
@@ -80,6 +80,22 @@ def test_unmodified_stage_scripts_under_the_shim(tmp_path, monkeypatch, stage, m
     renders = [c for c in calls if c[0] == "render"]
     assert len(renders) == 1 and renders[0][3] == 8192 and renders[0][5] == getattr(L, model_name)
     assert renders[0][1].size == n and os.path.exists(tmp_path / "outputs" / f"{stage}.png")
+
+
+def test_unmodified_early_stage_scripts_under_the_shim(tmp_path, monkeypatch):
+    """Stages 4 and 5 (4_objects, 5_anti_aliasing: normals as colours) name no BSDF: one lattice ray per pixel and no
+    `spp` in stage 4, 100 jittered samples in stage 5; neither calls post_processing()."""
+    import learn_path_tracing_b200 as L
+    if not os.path.exists(os.path.join(REF, "4_objects", "__main__.py")):
+        pytest.skip("reference checkout not mounted")
+    g, calls = _run("4_objects", tmp_path, monkeypatch)
+    (r,) = [c for c in calls if c[0] == "render"]
+    assert (r[3], r[4], r[5], r[8]) == (1, 1, L.PT_SHADE_V2_NORMALS, L.PT_FLAG_PIXEL_GRID) and r[1].size == 2
+    assert calls[-1] == ("read", None, 1)
+    g, calls = _run("5_anti_aliasing", tmp_path, monkeypatch)
+    (r,) = [c for c in calls if c[0] == "render"]
+    assert (r[3], r[4], r[5], r[8]) == (100, 1, L.PT_SHADE_V2_NORMALS, 0)
+    assert calls[-1] == ("read", None, 100) and os.path.exists(tmp_path / "outputs" / "5_anti_aliasing.png")
 
 
 @pytest.mark.gpu
