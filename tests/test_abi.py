@@ -48,10 +48,11 @@ def test_no_cpu_fallback_without_a_gpu():
 
 
 def test_product_package_never_touches_the_oracle():
-    pkg = os.path.join(ROOT, "learn_path_tracing_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
-                text = open(os.path.join(dirpath, f)).read()
-                assert "ptoracle" not in text and "libptoracle" not in text, f
-                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+    """The package AND the drop-in layer above it (compat/: shim + drivers) never import, load or execute the oracle."""
+    for pkg in (os.path.join(ROOT, "learn_path_tracing_b200"), os.path.join(ROOT, "compat")):
+        for dirpath, _, files in os.walk(pkg):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    text = open(os.path.join(dirpath, f)).read()
+                    assert "ptoracle" not in text and "libptoracle" not in text, f
+                    assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
