@@ -173,6 +173,11 @@ PT_DEV void texel_accum(const SceneView& sv, const float* lut, int x, int y, flo
         o.normal.z = fmaf(wgt, ln[(q.y >> 16) & 255u], o.normal.z);
     }
 }
+// The four taps of a bilinear lookup, straight-line: a tap outside the field reads a clamped address and gets weight 0
+// ("reads outside the field are 0", as the reference's out-of-range field access) instead of branching around its load.
+// With one early-return branch per tap (round 1) the compiler could not move a load across the reconvergence point, so
+// the four L2 loads of a lookup ran one after the other; now all four are in flight together.  Same taps, same order
+// of accumulation, fma(0, x, o) = o: the result is bit-identical.
 PT_DEV Texel sample_texture(const SceneView& sv, const float* lut, int id, float u, float v, bool want_normal) {
     Texel o;
     o.albedo = f3(0, 0, 0); o.normal = f3(0, 0, 0); o.roughness = 0.0f; o.metallic = 0.0f;
@@ -182,10 +187,42 @@ PT_DEV Texel sample_texture(const SceneView& sv, const float* lut, int id, float
         o.normal = f3(0.0f, 0.0f, 1.0f);
     }
     const Taps k = bilinear_taps(__ldg(&sv.tex_areas[id]), u, v);
+#ifdef PT_OPT_BRANCHY_TAPS
     texel_accum(sv, lut, k.l, k.b, k.lb, want_normal, o);
     texel_accum(sv, lut, k.l, k.t, k.lt, want_normal, o);
     texel_accum(sv, lut, k.r, k.b, k.rb, want_normal, o);
     texel_accum(sv, lut, k.r, k.t, k.rt, want_normal, o);
+#else
+    const bool in_l = (unsigned)k.l < (unsigned)sv.tex_W, in_r = (unsigned)k.r < (unsigned)sv.tex_W;
+    const bool in_b = (unsigned)k.b < (unsigned)sv.tex_H, in_t = (unsigned)k.t < (unsigned)sv.tex_H;
+    const size_t row_l = (size_t)(in_l ? k.l : 0) * sv.tex_H, row_r = (size_t)(in_r ? k.r : 0) * sv.tex_H;
+    const int yb = in_b ? k.b : 0, yt = in_t ? k.t : 0;
+    const uint2 q0 = __ldcg(&sv.atlas[row_l + yb]), q1 = __ldcg(&sv.atlas[row_l + yt]);   // L2 only: the atlas must not
+    const uint2 q2 = __ldcg(&sv.atlas[row_r + yb]), q3 = __ldcg(&sv.atlas[row_r + yt]);   // evict BVH nodes from L1
+    const float w0 = in_l && in_b ? k.lb : 0.0f, w1 = in_l && in_t ? k.lt : 0.0f;
+    const float w2 = in_r && in_b ? k.rb : 0.0f, w3 = in_r && in_t ? k.rt : 0.0f;
+    const float* la = lut;
+    const float* ls = lut + 256;
+    const uint2 q[4] = {q0, q1, q2, q3};
+    const float w[4] = {w0, w1, w2, w3};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        o.albedo.x = fmaf(w[i], la[q[i].x & 255u], o.albedo.x);
+        o.albedo.y = fmaf(w[i], la[(q[i].x >> 8) & 255u], o.albedo.y);
+        o.albedo.z = fmaf(w[i], la[(q[i].x >> 16) & 255u], o.albedo.z);
+        o.roughness = fmaf(w[i], ls[q[i].x >> 24], o.roughness);
+        o.metallic = fmaf(w[i], ls[q[i].y >> 24], o.metallic);
+    }
+    if (want_normal) {
+        const float* ln = lut + 512;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            o.normal.x = fmaf(w[i], ln[q[i].y & 255u], o.normal.x);
+            o.normal.y = fmaf(w[i], ln[(q[i].y >> 8) & 255u], o.normal.y);
+            o.normal.z = fmaf(w[i], ln[(q[i].y >> 16) & 255u], o.normal.z);
+        }
+    }
+#endif
     return o;
 }
 PT_DEV float3 env_fetch(const SceneView& sv, int x, int y) {
@@ -204,8 +241,20 @@ PT_DEV float3 environment_color(const SceneView& sv, float3 d) {  // 15_module.p
     const float u = (theta * (1.0f / PT_PI) + 1.0f) * 0.5f;
     const float v = phi * (1.0f / PT_PI) + 0.5f;
     const Taps k = bilinear_taps(sv.env_area, u, v);
+#ifdef PT_OPT_BRANCHY_TAPS
     return k.lb * env_fetch(sv, k.l, k.b) + k.lt * env_fetch(sv, k.l, k.t) + k.rb * env_fetch(sv, k.r, k.b) +
            k.rt * env_fetch(sv, k.r, k.t);
+#else
+    const bool in_l = (unsigned)k.l < (unsigned)sv.env_W, in_r = (unsigned)k.r < (unsigned)sv.env_W;
+    const bool in_b = (unsigned)k.b < (unsigned)sv.env_H, in_t = (unsigned)k.t < (unsigned)sv.env_H;
+    const size_t row_l = (size_t)(in_l ? k.l : 0) * sv.env_H, row_r = (size_t)(in_r ? k.r : 0) * sv.env_H;
+    const int yb = in_b ? k.b : 0, yt = in_t ? k.t : 0;
+    const float4 e0 = __ldcg(&sv.env[row_l + yb]), e1 = __ldcg(&sv.env[row_l + yt]);
+    const float4 e2 = __ldcg(&sv.env[row_r + yb]), e3 = __ldcg(&sv.env[row_r + yt]);
+    const float3 z = f3(0, 0, 0);   // selects, not weights: an HDR texel may be anything, 0 * inf would not be 0
+    return k.lb * (in_l && in_b ? f3(e0) : z) + k.lt * (in_l && in_t ? f3(e1) : z) + k.rb * (in_r && in_b ? f3(e2) : z) +
+           k.rt * (in_r && in_t ? f3(e3) : z);
+#endif
 }
 
 // ---- legacy scatter ----------------------------------------------------------------------------
