@@ -53,3 +53,27 @@ def test_stale_ncu_counters_are_refused(tmp_path, monkeypatch):
     assert nc is None and "stale" in why
     (prof / "ncu_counters.json").write_text(json.dumps({"kernel_source_hash": "aaaa", "workloads": {"yoimiya_1080p": {"issue_active_pct": 70}}}))
     assert bench.ncu_counters("yoimiya_1080p")[0] == {"issue_active_pct": 70}
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_ours_arm_prints_the_contract_line_on_the_gpu():
+    """`bench.py --workload X --only` on the GPU: every key the driver reads is there, the roofline block carries the
+    achieved / peak / frac / traffic fields, e2e counts host<->device bytes, clocks were sampled during the timed region."""
+    p = _run({}, "--workload", "9_dof_720p", "--only", "--steps", "2", "--warmup", "3", "--no-cpu")
+    assert p.returncode == 0, p.stderr[-3000:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    need = (KEYS - {"impl"}) | {"clocks", "roofline", "roofline_fp32", "mrays_per_s", "workloads", "library"}
+    assert need <= set(line), need - set(line)
+    assert line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] == 3 and line["scaling"] == "strong"
+    assert line["config"] == bench.workload_config("9_dof_720p") and line["workloads"] == {}
+    r = line["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "avg_launch_ms"} <= set(r) and r["bound"] == "hbm"
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["unit"] == "GB/s"
+    e = line["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] == 1280 * 720 * 3 * 4
+    assert e["value"] <= 1.05 * line["value"]            # end to end cannot beat the device-resident rate
+    assert line["gpu_launches"] == 2 and line["value"] > 1000 and line["clocks"]["sm_max_mhz"]
+    assert line["library"]["kernel_source_hash"] == bench.kernel_source_hash()

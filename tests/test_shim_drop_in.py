@@ -110,3 +110,38 @@ def test_unmodified_10_final_script_renders_on_the_gpu(tmp_path, monkeypatch, ct
     ref = L.to_uint8(L.render(world, cam, spp=8192, propagate_limit=32, ctx=ctx))
     d = L.to_uint8(png).astype(np.int32) - ref.astype(np.int32)
     assert np.abs(d).max() <= 1 and (d != 0).mean() < 1e-3, (np.abs(d).max(), (d != 0).mean())
+
+
+def test_shim_flushes_per_camera_and_resets_on_fill(tmp_path, monkeypatch):
+    """Host logic of the shim's image field: samples booked for one (world, camera) collapse into one pass, a camera that
+    moved starts another pass with the sample index carried on, image.fill(0) starts over."""
+    for m in ("taichi", "dtypes", "camera", "world", "bsdf", "postprocessing", "_runtime"):
+        sys.modules.pop(m, None)
+    monkeypatch.syspath_prepend(SHIM)
+    import _runtime
+    from camera import Camera
+    from dtypes import Ray, Vec3f
+    from world import Sphere, World
+    import learn_path_tracing_b200 as L
+    calls = []
+    monkeypatch.setattr(_runtime, "_render_pass", lambda image, world, cam, count, depth, model, first, flags=0: calls.append((count, first, model, flags)))
+    monkeypatch.setattr(_runtime, "_read_image", lambda image: np.zeros(image.shape + (3,), np.float32))
+    image, rays = Vec3f.field(shape=(32, 16)), Ray.field(shape=(32, 16))
+    world = World([Sphere(Vec3f([0, 0, -2]), 0.5)])
+    cam = Camera((32, 16))
+    for k in range(5):
+        if k == 3:
+            cam.set_position(Vec3f([0, 1, 0]))            # the camera moves between samples 2 and 3
+        cam.get_rays(rays)
+        image.book(world, rays, 5, 8, L.PT_SHADE_V2)
+    assert image.to_numpy().shape == (32, 16, 3)
+    assert calls == [(3, 0, L.PT_SHADE_V2, 0), (2, 3, L.PT_SHADE_V2, 0)]
+    image.fill(0)
+    cam.get_rays(rays)
+    image.book(world, rays, 1, 8, L.PT_SHADE_V2_DIFFUSE)
+    image.to_numpy()
+    assert calls[-1] == (1, 0, L.PT_SHADE_V2_DIFFUSE, 0)
+    with pytest.raises(RuntimeError):
+        image.book(world, Ray.field(shape=(32, 16)), 1, 8, L.PT_SHADE_V2)   # shader() before get_rays()
+    for m in ("taichi", "dtypes", "camera", "world", "bsdf", "postprocessing", "_runtime"):
+        sys.modules.pop(m, None)
