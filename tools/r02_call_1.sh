@@ -1,3 +1,4 @@
+# record of GPU call 1 of round 2 (ran against the round-1 bench.py, which still had --wide; the 4-wide walk now lives in libb200pt_exp.so)
 set -x
 mkdir -p gpurun_out/r2a
 PT_TEST_WIDE_RENDER=1 timeout 600 python -m pytest tests -m gpu -x -q -k "wide" > gpurun_out/r2a/wide_tests.txt 2>&1
