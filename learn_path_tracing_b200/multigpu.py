@@ -8,9 +8,10 @@ then summed onto rank 0 with torch.distributed.reduce (NCCL over NVLink; gloo in
 runs the fused divide-by-spp + tonemap kernel.
 
 Nothing on this path waits for the GPU on the host: pt_render is enqueued without statistics, the reduce follows on
-the same stream, and the only synchronisation is rank 0's read of the finished image.  With `bands` > 1 the frame is
-rendered in horizontal bands and the reduce of band k runs on a side stream while band k + 1 renders, so only the
-last band's reduce is exposed (strong scaling of short frames: 8_refract at 32 spp per GPU is a 3.7 ms render).
+the same stream, and the only synchronisation is rank 0's read of the finished image.  `bands` > 1 renders the frame in
+horizontal bands and reduces band k on a side stream while band k + 1 renders; measured on 2 B200s this LOSES to one
+band (8_refract 34.9 / 33.6 / 31.5 Gpaths/s at 1 / 4 / 8 bands, Yoimiya 9.6 / 8.2 / 7.3): every band pays the ramp-up and
+tail of its own persistent launch while the reduce it hides is ~0.1 ms — so 1 is the default everywhere.
 Works for the v2 sphere worlds and for the legacy mesh worlds (the shading model follows the world type;
 legacy/PT_in_one_weekend/15_module.py:1022-1036 is the loop it replaces).
 """
